@@ -1,0 +1,158 @@
+"""Pins the CPU oracle against every golden artefact the reference ships for the hot path
+(SURVEY.md section 8c): two fp64 displacement fields, three sfepy log pins, the committed
+renders and the text formats."""
+import numpy as np
+import pytest
+
+from oracle import raster_oracle as ro
+from oracle.fea_oracle import (OracleProblem, facet_region_vertices, fix_orientation,
+                               plane_strain_D, element_stiffness, points_in_list)
+
+
+def _application(golden, name):
+    co, cn = golden[name + "_coors"], golden[name + "_conn"]
+    p = OracleProblem(co, cn, num_steps=2)
+    if name == "cantilever":   # applications/cantilever/cantilever.py:43-72
+        v0, fv, mag = np.where(co[:, 0] < 0.01)[0], 3, (0.0, -1000.0)
+    else:                      # applications/shearblade/shearblade.py:43-72
+        v0, fv, mag = np.where(co[:, 1] > 0.74)[0], 1, (100.0, 3000.0)
+    p.fixed_vertex[:] = False
+    p.fixed_vertex[facet_region_vertices(p.conn, v0, len(co))] = True
+    p.load[:] = 0
+    p.load[fv] = mag
+    return p
+
+
+@pytest.mark.parametrize("name,nfix,n,nnz", [("cantilever", 42, 4844, 65896),
+                                             ("shearblade", 194, 10466, 144084)])
+def test_golden_displacement(golden, name, nfix, n, nnz):
+    p = _application(golden, name)
+    assert np.array_equal(golden[name + "_vtk_points"][:, :2], p.coors)  # A-1
+    assert np.array_equal(p.conn, golden[name + "_vtk_cells"])          # A-2 orientation fix
+    assert int(p.fixed_vertex.sum()) == nfix
+    A = p.stiffness()
+    assert A.shape == (n, n) and A.nnz == nnz                           # sfepy log pin / App. B
+    g = golden[name + "_u"]
+    assert np.all(g[:, 2] == 0)                                         # A-15 padding
+    for mode in ("reference", "best"):
+        u = p.solve(mode)[-1]
+        rel = np.linalg.norm(u - g[:, :2]) / np.linalg.norm(g[:, :2])
+        assert rel <= 1e-10, (mode, rel)
+    assert np.all(u[p.fixed_vertex] == 0)
+
+
+def test_shearblade_residual_pin(golden, golden_meta):
+    p = _application(golden, "shearblade")
+    assert p.n_flipped == len(p.conn)                                   # CW mesh (F12)
+    r0 = np.linalg.norm(p.rhs_final())
+    assert abs(r0 - golden_meta["pins"]["shearblade"]["r0"]) < 1e-3
+
+
+def test_composite_log_pins(golden, golden_meta):
+    """F2 (RHS applied once per region), F4 (complete cells only), A-6, A-18."""
+    co, cn = golden["composite_coors"], golden["composite_conn"]
+    concrete = co[co[:, 1] > 0.6875]
+    steel = co[co[:, 1] <= 0.6875]
+    assert (len(concrete), len(steel)) == (2712, 7126)
+    p = OracleProblem(
+        co, cn,
+        force_vertex_tags_magnitudes=[(6, (0, -200)), (7, (0, -200)), (8, (0, -200)), (9, (0, -200))],
+        constraints_vertex_tags=[2, 3], num_steps=2,
+        material_properties_to_vertices={(30000, 0.2): concrete, (210000, 0.3): steel})
+    pins = golden_meta["pins"]["composite"]
+    A = p.stiffness()
+    assert len(cn) == pins["cells"]
+    assert A.shape == (pins["shape"],) * 2
+    assert A.nnz == pins["nnz"]
+    assert abs(np.linalg.norm(p.rhs_final()) - pins["r0"]) < 1e-9
+    assert "\n".join(p.magnitudes_lines) + "\n" == golden_meta["composite_magnitudes"]
+    assert "\n".join(p.materials_lines) + "\n" == golden_meta["composite_materials"]
+    # the committed outputs came from a singular system: the classifier must say so
+    assert p.classify()["well_posed"] == 0 and p.overlap_cells() == 0
+
+
+def test_ranges_format(golden_meta):
+    line = golden_meta["composite_ranges"].splitlines()[0]
+    name, val = line.split(":")
+    assert name == "displacement_x_1"
+    lo, hi = eval(val)
+    assert "%s:%s" % (name, str((lo, hi))) == line
+
+
+def test_plane_strain_not_stress():
+    D = plane_strain_D(210000.0, 0.3)
+    lam = 210000 * 0.3 / (1.3 * 0.4)
+    mu = 210000 / 2.6
+    assert np.allclose(D, [[lam + 2 * mu, lam, 0], [lam, lam + 2 * mu, 0], [0, 0, mu]], rtol=1e-15)
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_element_stiffness_properties(k):
+    """Symmetry, rigid-body null space, positive semi-definiteness (P1 and unpinned Q1)."""
+    rng = np.random.default_rng(0)
+    if k == 3:
+        X = np.array([[0, 0], [1, 0], [0, 1.0]])
+    else:
+        X = np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]])
+    X = X + 0.1 * rng.standard_normal(X.shape)
+    Ke = element_stiffness(X, np.arange(k, dtype=np.int32)[None], plane_strain_D(1000.0, 0.3))[0]
+    assert np.allclose(Ke, Ke.T, atol=1e-9)
+    tx = np.tile([1.0, 0.0], k)
+    ty = np.tile([0.0, 1.0], k)
+    rot = np.stack([-X[:, 1], X[:, 0]], axis=1).ravel()
+    for m in (tx, ty, rot):
+        assert np.abs(Ke @ m).max() < 1e-9
+    w = np.linalg.eigvalsh(Ke)
+    assert w.min() > -1e-9 and (w > 1e-6).sum() == 2 * k - 3
+
+
+def test_q1_matches_two_p1_on_affine_field():
+    """A bilinear quad reproduces a linear displacement field exactly: K_e u_lin equals the
+    consistent nodal forces of a constant stress, same as the two-triangle split."""
+    X = np.array([[0, 0], [2, 0], [2, 1], [0, 1.0]])
+    D = plane_strain_D(100.0, 0.25)
+    G = np.array([[0.01, 0.02], [-0.03, 0.005]])
+    u = (X @ G.T).ravel()
+    Kq = element_stiffness(X, np.array([[0, 1, 2, 3]], dtype=np.int32), D)[0]
+    Kt = np.zeros((8, 8))
+    for tri in ([0, 1, 2], [0, 2, 3]):
+        ke = element_stiffness(X, np.array([tri], dtype=np.int32), D)[0]
+        d = np.array([[2 * v, 2 * v + 1] for v in tri]).ravel()
+        Kt[np.ix_(d, d)] += ke
+    assert np.allclose(Kq @ u, Kt @ u, atol=1e-12)
+
+
+def test_points_in_list_is_per_scalar():
+    co = np.array([[0.0, 1.0], [1.0, 0.0], [0.5, 0.25], [0.25, 0.5]])
+    # (0.5, 0.25) is listed; (0.25, 0.5) matches per scalar even though the pair is not listed
+    assert list(points_in_list(co, [(0.5, 0.25)])) == [2, 3]
+
+
+@pytest.mark.parametrize("name,window,bounds", [("cantilever", 540, (13, 526)),
+                                                ("shearblade", 591, (39, 551))])
+def test_window_and_raster_pins(golden, name, window, bounds):
+    """Closed-form camera + two-pass sizing reproduces the committed renders
+    (test_nbs/generateapplication.ipynb cells 6-7: initial window 756, image size 512,
+    clim +-0.05)."""
+    co = golden[name + "_coors"]
+    cn, _ = fix_orientation(co, golden[name + "_conn"])
+    bbox = (co[:, 0].min(), co[:, 1].min(), co[:, 0].max(), co[:, 1].max())
+    W, b = ro.closed_form_window(bbox, 512, initial=756)
+    assert W == window == golden[name + "_png_outline"].shape[0]
+    assert (b[0], b[2]) == bounds
+    size = b[2] - b[0]
+    aff = ro.pixel_affine(bbox, W, b)
+    for c, nm in enumerate(("displacement_x", "displacement_y")):
+        ref = golden["%s_png_%s" % (name, nm)]
+        assert ref.shape[:2] == (size, size)
+        assert np.array_equal(ref[:, :, 0], ref[:, :, 1]) and np.array_equal(ref[:, :, 0], ref[:, :, 2])
+        img = ro.rasterize_scalar(co, cn, golden[name + "_u"][:, c], size, aff, clim=(-0.05, 0.05))
+        g = ref[:, :, 0].astype(int)
+        inter = (img != 255) & (g != 255)
+        m = inter.copy()
+        m[1:] &= inter[:-1]; m[:-1] &= inter[1:]; m[:, 1:] &= inter[:, :-1]; m[:, :-1] &= inter[:, 1:]
+        d = np.abs(img.astype(int) - g)[m]
+        assert (d <= 1).mean() >= 0.997, (nm, (d <= 1).mean())
+        assert (d == 0).mean() >= 0.85
+        cov = ((img != 255) != (g != 255)).sum() / max(1, (g != 255).sum())
+        assert cov < 0.02
