@@ -1,0 +1,617 @@
+// C-ABI of libfea_b200.so (see include/fea_b200.h): context and batch life cycle, host<->device
+// transfers, orchestration of the kernel stages, CUDA-graph driven lock-step PCG loop.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "fea_internal.cuh"
+
+using namespace fea;
+
+struct fea_ctx {
+  Ctx c;
+  int32_t* h_flag = nullptr;  // pinned [4]
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+};
+struct fea_batch {
+  Batch b;
+  fea_ctx* owner = nullptr;
+};
+
+namespace {
+
+constexpr int kChunk = 32;      // PCG iterations between host polls (even)
+constexpr int kMaxTimed = 64;   // event-timed iterations per solve
+
+int fail(fea_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    char buf[512];
+    if (e != cudaSuccess)
+      snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+      snprintf(buf, sizeof buf, "%s", what);
+    ctx->c.err = buf;
+  }
+  if (e != cudaSuccess) cudaGetLastError();  // clear sticky-less errors
+  return code;
+}
+
+#define CK(ctx, call)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess)                                                   \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, #call, e_); \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(Batch& b, T** p, int64_t n) {
+  *p = nullptr;
+  if (n <= 0) n = 1;
+  cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (size_t)n, b.ctx->stream);
+  if (e == cudaSuccess) b.allocs.push_back(*p);
+  return e;
+}
+
+__global__ void k_gather_i32(const int32_t* __restrict__ src, const int64_t* __restrict__ idx, int n,
+                             int32_t* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void k_localize_conn(int64_t NC, int npc, const int64_t* __restrict__ cell_off,
+                                const int64_t* __restrict__ vtx_off, int ns, const int32_t* __restrict__ conn,
+                                int32_t* __restrict__ out) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  const int s = seg_of(cell_off, ns, c);
+  for (int a = 0; a < npc; ++a) out[c * npc + a] = (int32_t)(conn[c * npc + a] - vtx_off[s]);
+}
+
+void free_batch(fea_batch* hb) {
+  if (!hb) return;
+  Batch& b = hb->b;
+  cudaSetDevice(b.ctx->device);
+  for (void* p : b.allocs) cudaFreeAsync(p, b.ctx->stream);
+  b.allocs.clear();
+  delete hb;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fea_version(int* major, int* minor) {
+  if (major) *major = FEA_VERSION_MAJOR;
+  if (minor) *minor = FEA_VERSION_MINOR;
+  return FEA_OK;
+}
+
+int fea_ctx_create(int device, fea_ctx** out) {
+  if (!out) return FEA_BAD_ARG;
+  *out = nullptr;
+  fea_ctx* ctx = new (std::nothrow) fea_ctx();
+  if (!ctx) return FEA_OUT_OF_MEMORY;
+  ctx->c.device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
+  if ((e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
+  cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  if (cudaHostAlloc((void**)&ctx->h_flag, 4 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+    cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+    return FEA_CUDA_ERROR;
+  }
+  cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming);
+  cudaEventCreate(&ctx->ev_t0);
+  cudaEventCreate(&ctx->ev_t1);
+  ctx->events.resize(3 * kMaxTimed);
+  for (auto& ev : ctx->events) cudaEventCreate(&ev);
+  *out = ctx;
+  return FEA_OK;
+}
+
+int fea_ctx_destroy(fea_ctx* ctx) {
+  if (!ctx) return FEA_OK;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  for (auto& ev : ctx->events) cudaEventDestroy(ev);
+  cudaEventDestroy(ctx->ev_poll[0]);
+  cudaEventDestroy(ctx->ev_poll[1]);
+  cudaEventDestroy(ctx->ev_t0);
+  cudaEventDestroy(ctx->ev_t1);
+  cudaFreeHost(ctx->h_flag);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return FEA_OK;
+}
+
+const char* fea_last_error(const fea_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
+
+int fea_host_alloc(fea_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return FEA_BAD_ARG;
+  cudaSetDevice(ctx->c.device);
+  CK(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return FEA_OK;
+}
+int fea_host_free(fea_ctx* ctx, void* p) {
+  if (!ctx) return FEA_BAD_ARG;
+  if (p) CK(ctx, cudaFreeHost(p));
+  return FEA_OK;
+}
+int fea_ctx_synchronize(fea_ctx* ctx) {
+  if (!ctx) return FEA_BAD_ARG;
+  CK(ctx, cudaStreamSynchronize(ctx->c.stream));
+  return FEA_OK;
+}
+
+// ---------------------------------------------------------------------------
+int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
+  if (!ctx || !d || !out) return FEA_BAD_ARG;
+  *out = nullptr;
+  if (d->n_samples <= 0 || d->n_samples > kMaxSamplesPerBatch) return fail(ctx, FEA_BAD_ARG, "n_samples out of range");
+  if (d->nodes_per_cell != 3 && d->nodes_per_cell != 4) return fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
+  if (!d->vtx_off || !d->cell_off || !d->reg_off || !d->xy || !d->conn || !d->cell_region || !d->D || !d->fixed || !d->rhs)
+    return fail(ctx, FEA_BAD_ARG, "null array in fea_batch_desc");
+  const int ns = d->n_samples;
+  if (d->vtx_off[0] != 0 || d->cell_off[0] != 0 || d->reg_off[0] != 0) return fail(ctx, FEA_BAD_ARG, "offset tables must start at 0");
+  for (int s = 0; s < ns; ++s)
+    if (d->vtx_off[s + 1] < d->vtx_off[s] || d->cell_off[s + 1] < d->cell_off[s] || d->reg_off[s + 1] < d->reg_off[s])
+      return fail(ctx, FEA_BAD_ARG, "offset tables must be non-decreasing");
+  if (d->vtx_off[ns] >= (1LL << 30) || d->cell_off[ns] >= (1LL << 29)) return fail(ctx, FEA_BAD_ARG, "batch too large for 32-bit indices");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  fea_batch* hb = new (std::nothrow) fea_batch();
+  if (!hb) return fail(ctx, FEA_OUT_OF_MEMORY, "host allocation");
+  hb->owner = ctx;
+  Batch& b = hb->b;
+  b.ctx = &ctx->c;
+  b.h_flag = ctx->h_flag;
+  b.ns = ns;
+  b.npc = d->nodes_per_cell;
+  b.vtx_off.assign(d->vtx_off, d->vtx_off + ns + 1);
+  b.cell_off.assign(d->cell_off, d->cell_off + ns + 1);
+  b.reg_off.assign(d->reg_off, d->reg_off + ns + 1);
+  b.NV = b.vtx_off[ns];
+  b.NC = b.cell_off[ns];
+  b.NREG = b.reg_off[ns];
+  b.NBR = 0;
+  for (int s = 0; s < ns; ++s) {
+    const int64_t nv = b.vtx_off[s + 1] - b.vtx_off[s];
+    b.NBR += (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
+  }
+  cudaStream_t st = ctx->c.stream;
+  int32_t* conn_local = nullptr;
+  int8_t* creg_local = nullptr;
+  cudaError_t e = cudaSuccess;
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(dalloc(b, &b.xy, b.NV * 2));
+  A(dalloc(b, &b.conn, b.NC * b.npc));
+  A(dalloc(b, &b.cell_dreg, b.NC));
+  A(dalloc(b, &b.D, (int64_t)b.NREG * 9));
+  A(dalloc(b, &b.fixed, b.NV));
+  A(dalloc(b, &b.rhs, b.NV * 2));
+  A(dalloc(b, &b.d_vtx_off, ns + 1));
+  A(dalloc(b, &b.d_cell_off, ns + 1));
+  A(dalloc(b, &b.d_reg_off, ns + 1));
+  A(dalloc(b, &b.vsample, b.NV));
+  A(dalloc(b, &b.flips, ns));
+  A(dalloc(b, &b.vrank, b.NV));
+  A(dalloc(b, &b.n_active, ns));
+  A(dalloc(b, &b.row_base, ns + 1));
+  A(dalloc(b, &b.row_of_vertex, b.NV));
+  A(dalloc(b, &b.vertex_of_row, b.NBR));
+  A(dalloc(b, &b.sys_of_cta, b.NBR / kCtaRows));
+  A(dalloc(b, &b.cta_first, ns));
+  A(dalloc(b, &b.cta_count, ns));
+  A(dalloc(b, &b.err_flag, 4));
+  A(dalloc(b, &b.empty, ns));
+  A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
+  A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));
+  A(cudaMemcpyAsync(b.xy, d->xy, sizeof(double) * b.NV * 2, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(conn_local, d->conn, sizeof(int32_t) * b.NC * b.npc, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(creg_local, d->cell_region, b.NC, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.D, d->D, sizeof(double) * 9 * b.NREG, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.fixed, d->fixed, b.NV, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.rhs, d->rhs, sizeof(double) * b.NV * 2, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.d_vtx_off, b.vtx_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.d_cell_off, b.cell_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.d_reg_off, b.reg_off.data(), sizeof(int32_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemsetAsync(b.flips, 0, sizeof(int32_t) * ns, st));
+  A(cudaMemsetAsync(b.err_flag, 0, sizeof(int32_t) * 4, st));
+  A(cudaMemsetAsync(b.empty, 0, sizeof(int32_t) * ns, st));
+  A(cudaMemsetAsync(b.vertex_of_row, 0xFF, sizeof(int32_t) * std::max<int64_t>(1, b.NBR), st));
+  A(launch_setup(b, creg_local, conn_local));
+  if (conn_local) cudaFreeAsync(conn_local, st);
+  if (creg_local) cudaFreeAsync(creg_local, st);
+#undef A
+  if (e != cudaSuccess) {
+    int rc = fail(ctx, e == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, "fea_batch_create", e);
+    free_batch(hb);
+    return rc;
+  }
+  *out = hb;
+  return FEA_OK;
+}
+
+int fea_batch_destroy(fea_batch* hb) {
+  if (!hb) return FEA_OK;
+  free_batch(hb);
+  return FEA_OK;
+}
+
+int fea_batch_assemble(fea_batch* hb) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (b.assembled) return FEA_OK;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  const int N = 2 * b.npc;
+  CK(ctx, dalloc(b, &b.inc_ptr, b.NV + 1));
+  CK(ctx, dalloc(b, &b.inc, b.NC * b.npc));
+  CK(ctx, dalloc(b, &b.adj_ptr, b.NV + 1));
+  CK(ctx, dalloc(b, &b.ke, b.NC * N * N));
+  b.n_slices = (int32_t)(b.NBR / kSlice);
+  CK(ctx, dalloc(b, &b.slice_len, b.n_slices));
+  CK(ctx, dalloc(b, &b.slice_ptr, (int64_t)b.n_slices + 1));
+  CK(ctx, launch_element_stiffness(b));
+  CK(ctx, launch_topology_counts(b));
+  CK(ctx, launch_sell_lengths(b));
+  // one host round trip: totals and error flags
+  int32_t h_adj = 0, h_err[2] = {0, 0};
+  int64_t h_blocks = 0;
+  CK(ctx, cudaMemcpyAsync(&h_adj, b.adj_ptr + b.NV, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&h_blocks, b.slice_ptr + b.n_slices, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(h_err, b.err_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (h_err[0] & 2) return fail(ctx, FEA_MESH_ERROR, "connectivity or cell_region index out of range");
+  if (h_err[0] & 1) return fail(ctx, FEA_MESH_ERROR, "vertex valence exceeds the supported maximum (63)");
+  b.n_adj = h_adj;
+  b.n_blocks = b.n_slices ? h_blocks : 0;
+  b.max_row_blocks = h_err[1];
+  CK(ctx, dalloc(b, &b.adj, b.n_adj));
+  CK(ctx, launch_topology_fill(b));
+  CK(ctx, dalloc(b, &b.val, b.n_blocks * 2));
+  CK(ctx, dalloc(b, &b.col, b.n_blocks));
+  CK(ctx, dalloc(b, &b.dscale, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.x, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.r, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.p0, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.p1, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.q, b.NBR * 2));
+  const int64_t ncta = b.NBR / kCtaRows;
+  CK(ctx, dalloc(b, &b.partA, ncta));
+  CK(ctx, dalloc(b, &b.partB, ncta));
+  CK(ctx, dalloc(b, &b.sc.rz[0], b.ns));
+  CK(ctx, dalloc(b, &b.sc.rz[1], b.ns));
+  CK(ctx, dalloc(b, &b.sc.pq, b.ns));
+  CK(ctx, dalloc(b, &b.sc.rz0, b.ns));
+  CK(ctx, dalloc(b, &b.sc.tol2, b.ns));
+  CK(ctx, dalloc(b, &b.sc.done, b.ns));
+  CK(ctx, dalloc(b, &b.sc.iters, b.ns));
+  CK(ctx, dalloc(b, &b.sc.status, b.ns));
+  CK(ctx, dalloc(b, &b.sc.cntA, b.ns));
+  CK(ctx, dalloc(b, &b.sc.cntB, b.ns));
+  CK(ctx, dalloc(b, &b.sc.n_done, 1));
+  CK(ctx, dalloc(b, &b.rz_last, b.ns));
+  CK(ctx, dalloc(b, &b.relres, b.ns));
+  CK(ctx, dalloc(b, &b.u, b.NV * 2));
+  CK(ctx, dalloc(b, &b.ranges, (int64_t)b.ns * 4));
+  CK(ctx, cudaMemsetAsync(b.sc.status, 0xFF, sizeof(int32_t) * b.ns, st));
+  CK(ctx, cudaMemsetAsync(b.sc.iters, 0, sizeof(int32_t) * b.ns, st));
+  CK(ctx, cudaMemsetAsync(b.relres, 0, sizeof(double) * b.ns, st));
+  CK(ctx, launch_sell_fill(b));
+  b.assembled = true;
+  return FEA_OK;
+}
+
+int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_solve before fea_batch_assemble");
+  if (!(rtol >= 0.0) || max_iter < 1) return fail(ctx, FEA_BAD_ARG, "rtol must be >= 0 and max_iter >= 1");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  b.stats = fea_solve_stats{};
+  int64_t launches = 0;
+  CK(ctx, cudaEventRecord(ctx->ev_t0, st));
+  CK(ctx, launch_pcg_init(b, rtol));
+  launches += 1;
+  // capture kChunk-2 iterations once; the first two iterations of every chunk are plain
+  // launches so that one spmv/update pair per chunk can be bracketed by timing events
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  CK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int i = 2; i < kChunk; ++i) {
+    launch_pcg_spmv(b, i & 1, st);
+    launch_pcg_update(b, i & 1, max_iter, st);
+  }
+  CK(ctx, cudaStreamEndCapture(st, &graph));
+  CK(ctx, cudaGraphInstantiate(&exec, graph, 0));
+  const int max_chunks = (max_iter + kChunk - 1) / kChunk + 1;
+  std::vector<int> done_after;  // n_done observed after chunk k
+  int timed = 0;
+  int k = 0;
+  cudaError_t e = cudaSuccess;
+  for (; k < max_chunks; ++k) {
+    if (timed < kMaxTimed) {
+      cudaEventRecord(ctx->events[3 * timed], st);
+      launch_pcg_spmv(b, 0, st);
+      cudaEventRecord(ctx->events[3 * timed + 1], st);
+      launch_pcg_update(b, 0, max_iter, st);
+      cudaEventRecord(ctx->events[3 * timed + 2], st);
+      ++timed;
+    } else {
+      launch_pcg_spmv(b, 0, st);
+      launch_pcg_update(b, 0, max_iter, st);
+    }
+    launch_pcg_spmv(b, 1, st);
+    launch_pcg_update(b, 1, max_iter, st);
+    e = cudaGraphLaunch(exec, st);
+    if (e != cudaSuccess) break;
+    launches += 2 * kChunk;
+    cudaMemcpyAsync(&b.h_flag[k & 1], b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(ctx->ev_poll[k & 1], st);
+    if (k >= 1) {
+      e = cudaEventSynchronize(ctx->ev_poll[(k - 1) & 1]);
+      if (e != cudaSuccess) break;
+      done_after.push_back(b.h_flag[(k - 1) & 1]);
+      if (b.h_flag[(k - 1) & 1] >= b.ns) { ++k; break; }
+    }
+  }
+  if (e == cudaSuccess) e = launch_finalize(b);
+  launches += 3;
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_t1, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_solve", e);
+  // statistics
+  std::vector<int32_t> it(b.ns), stt(b.ns);
+  CK(ctx, cudaMemcpy(it.data(), b.sc.iters, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemcpy(stt.data(), b.sc.status, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
+  b.stats.iterations = *std::max_element(it.begin(), it.end());
+  b.stats.n_converged = (int32_t)std::count(stt.begin(), stt.end(), (int32_t)FEA_SAMPLE_CONVERGED);
+  // average only over timed launches that ran with every system still active
+  double sa = 0, su = 0;
+  int na = 0;
+  for (int t = 0; t < timed; ++t) {
+    const bool all_active = (t == 0) || (t - 1 < (int)done_after.size() && done_after[t - 1] == 0);
+    if (!all_active) break;
+    float a = 0, u = 0;
+    cudaEventElapsedTime(&a, ctx->events[3 * t], ctx->events[3 * t + 1]);
+    cudaEventElapsedTime(&u, ctx->events[3 * t + 1], ctx->events[3 * t + 2]);
+    sa += a;
+    su += u;
+    ++na;
+  }
+  b.stats.spmv_launches_timed = na;
+  b.stats.update_launches_timed = na;
+  b.stats.spmv_ms_avg = na ? (float)(sa / na) : 0.f;
+  b.stats.update_ms_avg = na ? (float)(su / na) : 0.f;
+  cudaEventElapsedTime(&b.stats.solve_ms, ctx->ev_t0, ctx->ev_t1);
+  b.stats.kernel_launches = launches;
+  b.solved = true;
+  return FEA_OK;
+}
+
+int fea_batch_rasterize(fea_batch* hb, int32_t size, const double* affine, double value_scale) {
+  if (!hb || !affine) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize before fea_batch_solve");
+  if (size < 1 || size > 8192) return fail(ctx, FEA_BAD_ARG, "image size out of range");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  if (b.img_size != size) {
+    const int64_t per = (int64_t)size * size;
+    CK(ctx, dalloc(b, &b.images, (int64_t)b.ns * 2 * per));
+    CK(ctx, dalloc(b, &b.owner, (int64_t)b.ns * per));
+    if (!b.affine) CK(ctx, dalloc(b, &b.affine, (int64_t)b.ns * 4));
+    b.img_size = size;
+  }
+  CK(ctx, cudaMemcpyAsync(b.affine, affine, sizeof(double) * 4 * b.ns, cudaMemcpyHostToDevice, st));
+  CK(ctx, launch_raster(b, value_scale));
+  b.rasterized = true;
+  return FEA_OK;
+}
+
+int fea_batch_download(fea_batch* hb, double* u, double* ranges, int32_t* iters, double* relres, int32_t* status) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_download before fea_batch_solve");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  if (u) CK(ctx, cudaMemcpyAsync(u, b.u, sizeof(double) * 2 * b.NV, cudaMemcpyDeviceToHost, st));
+  if (ranges) CK(ctx, cudaMemcpyAsync(ranges, b.ranges, sizeof(double) * 4 * b.ns, cudaMemcpyDeviceToHost, st));
+  if (iters) CK(ctx, cudaMemcpyAsync(iters, b.sc.iters, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (relres) CK(ctx, cudaMemcpyAsync(relres, b.relres, sizeof(double) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (status) CK(ctx, cudaMemcpyAsync(status, b.sc.status, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  return FEA_OK;
+}
+
+int fea_batch_download_images(fea_batch* hb, uint8_t* images) {
+  if (!hb || !images) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.rasterized) return fail(ctx, FEA_BAD_STATE, "fea_batch_download_images before fea_batch_rasterize");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaMemcpyAsync(images, b.images, (size_t)b.ns * 2 * b.img_size * b.img_size, cudaMemcpyDeviceToHost, ctx->c.stream));
+  CK(ctx, cudaStreamSynchronize(ctx->c.stream));
+  return FEA_OK;
+}
+
+int fea_batch_sample_sizes(fea_batch* hb, int64_t* n_active_dofs, int64_t* nnz) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_sample_sizes before fea_batch_assemble");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  std::vector<int32_t> na(b.ns), ap(b.ns + 1);
+  int32_t* d_tmp = nullptr;
+  CK(ctx, cudaMallocAsync((void**)&d_tmp, sizeof(int32_t) * (b.ns + 1), st));
+  k_gather_i32<<<(b.ns + 1 + 255) / 256, 256, 0, st>>>(b.adj_ptr, b.d_vtx_off, b.ns + 1, d_tmp);
+  CK(ctx, cudaMemcpyAsync(ap.data(), d_tmp, sizeof(int32_t) * (b.ns + 1), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(na.data(), b.n_active, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  cudaFreeAsync(d_tmp, st);
+  for (int s = 0; s < b.ns; ++s) {
+    if (n_active_dofs) n_active_dofs[s] = 2 * (int64_t)na[s];
+    if (nnz) nnz[s] = 4 * (int64_t)(ap[s + 1] - ap[s]);
+  }
+  return FEA_OK;
+}
+
+int fea_batch_get_info(fea_batch* hb, fea_batch_info* out) {
+  if (!hb || !out) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_get_info before fea_batch_assemble");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  std::vector<int32_t> na(b.ns), fl(b.ns);
+  int64_t rows = 0;
+  CK(ctx, cudaMemcpy(na.data(), b.n_active, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemcpy(fl.data(), b.flips, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemcpy(&rows, b.row_base + b.ns, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  out->n_vertices = b.NV;
+  out->n_cells = b.NC;
+  out->n_active_dofs = 0;
+  out->n_flipped = 0;
+  for (int s = 0; s < b.ns; ++s) {
+    out->n_active_dofs += 2 * (int64_t)na[s];
+    out->n_flipped += fl[s];
+  }
+  out->nnz = 4 * b.n_adj;
+  out->block_rows = rows;
+  out->sell_blocks = b.n_blocks;
+  out->max_row_blocks = b.max_row_blocks;
+  return FEA_OK;
+}
+
+int fea_batch_get_solve_stats(fea_batch* hb, fea_solve_stats* out) {
+  if (!hb || !out) return FEA_BAD_ARG;
+  *out = hb->b.stats;
+  return FEA_OK;
+}
+
+int fea_batch_get_conn(fea_batch* hb, int32_t* conn, int32_t* n_flipped) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  if (conn && b.NC) {
+    int32_t* tmp = nullptr;
+    CK(ctx, cudaMallocAsync((void**)&tmp, sizeof(int32_t) * b.NC * b.npc, st));
+    k_localize_conn<<<(unsigned)((b.NC + 255) / 256), 256, 0, st>>>(b.NC, b.npc, b.d_cell_off, b.d_vtx_off, b.ns, b.conn, tmp);
+    CK(ctx, cudaMemcpyAsync(conn, tmp, sizeof(int32_t) * b.NC * b.npc, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(tmp, st);
+  }
+  if (n_flipped) {
+    CK(ctx, cudaMemcpyAsync(n_flipped, b.flips, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+  }
+  return FEA_OK;
+}
+
+int fea_batch_get_element_stiffness(fea_batch* hb, double* ke) {
+  if (!hb || !ke) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "element stiffness requested before fea_batch_assemble");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  const int N = 2 * b.npc;
+  CK(ctx, cudaMemcpyAsync(ke, b.ke, sizeof(double) * b.NC * N * N, cudaMemcpyDeviceToHost, ctx->c.stream));
+  CK(ctx, cudaStreamSynchronize(ctx->c.stream));
+  return FEA_OK;
+}
+
+int fea_batch_get_csr(fea_batch* hb, int32_t s, int32_t* indptr, int32_t* indices, double* data) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_get_csr before fea_batch_assemble");
+  if (s < 0 || s >= b.ns) return fail(ctx, FEA_BAD_ARG, "sample index out of range");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  int32_t na = 0, a0 = 0, a1 = 0;
+  CK(ctx, cudaMemcpyAsync(&na, b.n_active + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&a0, b.adj_ptr + b.vtx_off[s], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(&a1, b.adj_ptr + b.vtx_off[s + 1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  const int64_t n = 2 * (int64_t)na, nnz = 4 * (int64_t)(a1 - a0);
+  int32_t *d_ip = nullptr, *d_ix = nullptr;
+  double* d_dt = nullptr;
+  if (indptr) {
+    CK(ctx, cudaMallocAsync((void**)&d_ip, sizeof(int32_t) * (n + 1), st));
+    CK(ctx, cudaMemsetAsync(d_ip, 0, sizeof(int32_t) * (n + 1), st));
+  }
+  if (indices) CK(ctx, cudaMallocAsync((void**)&d_ix, sizeof(int32_t) * std::max<int64_t>(1, nnz), st));
+  if (data) CK(ctx, cudaMallocAsync((void**)&d_dt, sizeof(double) * std::max<int64_t>(1, nnz), st));
+  CK(ctx, launch_csr_export(b, s, d_ip, d_ix, d_dt));
+  if (indptr) CK(ctx, cudaMemcpyAsync(indptr, d_ip, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, st));
+  if (indices) CK(ctx, cudaMemcpyAsync(indices, d_ix, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, st));
+  if (data) CK(ctx, cudaMemcpyAsync(data, d_dt, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (d_ip) cudaFreeAsync(d_ip, st);
+  if (d_ix) cudaFreeAsync(d_ix, st);
+  if (d_dt) cudaFreeAsync(d_dt, st);
+  return FEA_OK;
+}
+
+int fea_batch_spmv(fea_batch* hb, int32_t s, const double* x, double* y) {
+  if (!hb || !x || !y) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_spmv before fea_batch_assemble");
+  if (s < 0 || s >= b.ns) return fail(ctx, FEA_BAD_ARG, "sample index out of range");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  int32_t na = 0;
+  CK(ctx, cudaMemcpyAsync(&na, b.n_active + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  const int64_t n = 2 * (int64_t)na;
+  double *dx = nullptr, *dy = nullptr;
+  CK(ctx, cudaMallocAsync((void**)&dx, sizeof(double) * std::max<int64_t>(1, n), st));
+  CK(ctx, cudaMallocAsync((void**)&dy, sizeof(double) * std::max<int64_t>(1, n), st));
+  CK(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  CK(ctx, launch_plain_spmv(b, s, dx, dy));
+  CK(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  cudaFreeAsync(dx, st);
+  cudaFreeAsync(dy, st);
+  b.solved = false;  // solver vectors were overwritten
+  return FEA_OK;
+}
+
+int fea_solve_batch(fea_ctx* ctx, const fea_batch_desc* desc, double rtol, int32_t max_iter, int32_t image_size,
+                    const double* affine, double value_scale, double* u, double* ranges, int32_t* iters,
+                    double* relres, int32_t* status, uint8_t* images, fea_solve_stats* stats) {
+  fea_batch* hb = nullptr;
+  int rc = fea_batch_create(ctx, desc, &hb);
+  if (rc != FEA_OK) return rc;
+  rc = fea_batch_assemble(hb);
+  if (rc == FEA_OK) rc = fea_batch_solve(hb, rtol, max_iter);
+  if (rc == FEA_OK && image_size > 0 && affine) rc = fea_batch_rasterize(hb, image_size, affine, value_scale);
+  if (rc == FEA_OK) rc = fea_batch_download(hb, u, ranges, iters, relres, status);
+  if (rc == FEA_OK && image_size > 0 && affine && images) rc = fea_batch_download_images(hb, images);
+  if (rc == FEA_OK && stats) *stats = hb->b.stats;
+  fea_batch_destroy(hb);
+  return rc;
+}
+
+}  // extern "C"

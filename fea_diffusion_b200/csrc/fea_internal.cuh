@@ -1,0 +1,170 @@
+// Internal declarations shared by the translation units of libfea_b200.so.
+// Layouts and kernels are described in DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "fea_b200.h"
+
+namespace fea {
+
+constexpr int kSlice = 32;      // block rows per SELL slice (= one warp)
+constexpr int kCtaRows = 128;   // block rows per CTA in the solver kernels
+constexpr int kMaxAdj = 64;     // supported vertex valence + 1
+constexpr int kMaxSamplesPerBatch = 1 << 20;
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+};
+
+// Per-system (sample) solver scalars, structure of arrays on device.
+struct SysScalars {
+  double* rz[2];     // r.z of the current / previous iterate (ping-pong by iteration parity)
+  double* pq;        // p.Ap of the current iterate
+  double* rz0;       // r0.z0
+  double* tol2;      // rtol^2 * rz0
+  int32_t* done;     // 0 = iterating, 1 = finished
+  int32_t* iters;
+  int32_t* status;
+  unsigned int* cntA;  // arrival counters of the last-block reductions
+  unsigned int* cntB;
+  int32_t* n_done;   // single counter: finished systems
+};
+
+struct Batch {
+  Ctx* ctx = nullptr;
+  int32_t ns = 0, npc = 3;
+  int64_t NV = 0, NC = 0;
+  int32_t NREG = 0;
+  std::vector<int64_t> vtx_off, cell_off;
+  std::vector<int32_t> reg_off;
+  std::vector<void*> allocs;
+  bool assembled = false, solved = false, rasterized = false;
+
+  // inputs on device
+  double* xy = nullptr;          // [NV*2]
+  int32_t* conn = nullptr;       // [NC*npc] GLOBAL vertex ids, orientation-fixed
+  int32_t* cell_dreg = nullptr;  // [NC] global index into D, or -1
+  double* D = nullptr;           // [NREG*9]
+  uint8_t* fixed = nullptr;      // [NV]
+  double* rhs = nullptr;         // [NV*2]
+  int64_t* d_vtx_off = nullptr;  // [ns+1]
+  int64_t* d_cell_off = nullptr; // [ns+1]
+  int32_t* d_reg_off = nullptr;  // [ns+1]
+  int32_t* vsample = nullptr;    // [NV]
+  int32_t* flips = nullptr;      // [ns]
+  // equation map
+  int32_t* vrank = nullptr;      // [NV] rank among active vertices of the sample, -1 if fixed
+  int32_t* n_active = nullptr;   // [ns] active vertices
+  int64_t* row_base = nullptr;   // [ns+1] first (padded) block row of each sample
+  int64_t NBR = 0;               // allocated block rows (upper bound, multiple of kCtaRows)
+  int32_t* row_of_vertex = nullptr;  // [NV]
+  int32_t* vertex_of_row = nullptr;  // [NBR]
+  int32_t* sys_of_cta = nullptr;     // [NBR/kCtaRows]
+  int32_t* cta_first = nullptr;      // [ns] first CTA of the system
+  int32_t* cta_count = nullptr;      // [ns]
+  // topology
+  int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
+  int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending
+  int32_t* adj_ptr = nullptr;    // [NV+1] vertex adjacency over active vertices (sorted)
+  int32_t* adj = nullptr;
+  int64_t n_adj = 0;
+  int32_t* err_flag = nullptr;   // device error flag (valence overflow etc.)
+  // element matrices
+  double* ke = nullptr;          // [NC*(2*npc)^2]
+  // scaled block-SELL matrix
+  int32_t n_slices = 0;
+  int32_t* slice_len = nullptr;  // [n_slices]
+  int64_t* slice_ptr = nullptr;  // [n_slices+1] in block entries
+  int64_t n_blocks = 0;
+  double2* val = nullptr;        // [n_blocks*2]  per (slice,j): 32 top rows then 32 bottom rows
+  int32_t* col = nullptr;        // [n_blocks]
+  double* dscale = nullptr;      // [NBR*2] 1/sqrt(diag)
+  int32_t max_row_blocks = 0;
+  // solver vectors [NBR*2]
+  double *x = nullptr, *r = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr;
+  double *partA = nullptr, *partB = nullptr;  // [NBR/kCtaRows]
+  SysScalars sc{};
+  double* rz_last = nullptr;   // [ns] r.z at exit
+  double* relres = nullptr;    // [ns]
+  int32_t* empty = nullptr;    // [ns] 1 = an active vertex has no stiffness (A-18)
+  // outputs
+  double* u = nullptr;       // [NV*2]
+  double* ranges = nullptr;  // [ns*4]
+  int32_t img_size = 0;
+  uint8_t* images = nullptr; // [ns*2*size*size]
+  int32_t* owner = nullptr;  // [ns*size*size]
+  double* affine = nullptr;  // [ns*4]
+  fea_solve_stats stats{};
+  // pinned host scratch
+  int32_t* h_flag = nullptr;
+};
+
+// ---- launchers implemented in the kernel translation units -----------------
+// All return cudaError_t of the launch (cudaGetLastError).
+cudaError_t launch_setup(Batch& b, const int8_t* d_cell_region_local, const int32_t* d_conn_local);
+cudaError_t launch_topology_counts(Batch& b);                 // incidence + adjacency counts
+cudaError_t launch_topology_fill(Batch& b);                   // adjacency fill
+cudaError_t launch_element_stiffness(Batch& b);
+cudaError_t launch_sell_lengths(Batch& b);                    // slice_len + slice_ptr
+cudaError_t launch_sell_fill(Batch& b);                       // dscale, val, col
+cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d_indices,
+                              double* d_data);
+cudaError_t launch_pcg_init(Batch& b, double rtol);
+cudaError_t launch_pcg_spmv(Batch& b, int parity, cudaStream_t st);
+cudaError_t launch_pcg_update(Batch& b, int parity, int max_iter, cudaStream_t st);
+cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
+cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
+cudaError_t launch_raster(Batch& b, double value_scale);
+
+// scans (device-wide, deterministic)
+cudaError_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tmp,
+                               cudaStream_t st);  // out[n] = total; tmp >= n/4096+2 ints
+cudaError_t exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, int64_t mul,
+                                      int64_t* tmp, cudaStream_t st);
+
+}  // namespace fea
+
+// ---- device helpers --------------------------------------------------------
+#ifdef __CUDACC__
+namespace fea {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// streaming 16-byte load that does not allocate in L1 (matrix values, read once per kernel)
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// binary search: largest s with off[s] <= i   (off has n+1 entries, off[0] = 0)
+__device__ __forceinline__ int seg_of(const int64_t* off, int n, int64_t i) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace fea
+#endif

@@ -1,0 +1,150 @@
+// K6: rasterisation of the step-1 displacement components to the displacement_x / displacement_y
+// gray images -- replaces custom_plotter.plot -> pyvista -> VTK off-screen rendering
+// (reference datagen/fea_analysis.py:526-613, datagen/custom_plotter.py:121-193; SURVEY A-16).
+//
+// Semantics (identical to oracle/raster_oracle.py, operation for operation): a pixel is sampled
+// at its centre; it belongs to the lowest-index triangle that contains the centre (edges
+// inclusive); the scalar is interpolated barycentrically, normalised by the sample's own
+// [min, max], and mapped through the 'binary' LUT: gray = 255 - min(floor(256 t), 255);
+// background 255.  All coordinate arithmetic uses the *_rn intrinsics so that no FMA
+// contraction can make coverage differ from the numpy oracle.
+#include "fea_internal.cuh"
+
+namespace fea {
+
+__global__ void k_owner_init(int64_t n, int32_t* __restrict__ owner) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) owner[i] = 0x7fffffff;
+}
+
+struct Tri {
+  double X[3], Y[3];
+};
+
+__device__ __forceinline__ void bary(const Tri& t, double qx, double qy, double w[3], double* area2) {
+  const double ax = t.X[0], bx = t.X[1], cx = t.X[2];
+  const double ay = t.Y[0], by = t.Y[1], cy = t.Y[2];
+  double wa = __dsub_rn(__dmul_rn(__dsub_rn(bx, qx), __dsub_rn(cy, qy)), __dmul_rn(__dsub_rn(cx, qx), __dsub_rn(by, qy)));
+  double wb = __dsub_rn(__dmul_rn(__dsub_rn(cx, qx), __dsub_rn(ay, qy)), __dmul_rn(__dsub_rn(ax, qx), __dsub_rn(cy, qy)));
+  double wc = __dsub_rn(__dmul_rn(__dsub_rn(ax, qx), __dsub_rn(by, qy)), __dmul_rn(__dsub_rn(bx, qx), __dsub_rn(ay, qy)));
+  double a2 = __dsub_rn(__dmul_rn(__dsub_rn(bx, ax), __dsub_rn(cy, ay)), __dmul_rn(__dsub_rn(cx, ax), __dsub_rn(by, ay)));
+  const double sgn = a2 < 0.0 ? -1.0 : 1.0;
+  w[0] = __dmul_rn(wa, sgn);
+  w[1] = __dmul_rn(wb, sgn);
+  w[2] = __dmul_rn(wc, sgn);
+  *area2 = __dmul_rn(a2, sgn);
+}
+
+template <int NPC>
+__device__ __forceinline__ void load_tri(int64_t cell, int sub, const int32_t* __restrict__ conn,
+                                         const double* __restrict__ xy, const double* __restrict__ aff,
+                                         Tri& t, int32_t vid[3]) {
+  const int l0 = 0, l1 = (NPC == 3) ? 1 : (sub ? 2 : 1), l2 = (NPC == 3) ? 2 : (sub ? 3 : 2);
+  const int ls[3] = {l0, l1, l2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int32_t v = conn[cell * NPC + ls[k]];
+    vid[k] = v;
+    t.X[k] = __dadd_rn(__dmul_rn(xy[2 * (int64_t)v], aff[0]), aff[1]);
+    t.Y[k] = __dadd_rn(__dmul_rn(xy[2 * (int64_t)v + 1], aff[2]), aff[3]);
+  }
+}
+
+template <int NPC>
+__global__ void k_raster_cover(int64_t NT, const int64_t* __restrict__ cell_off, int ns,
+                               const int32_t* __restrict__ conn, const double* __restrict__ xy,
+                               const double* __restrict__ affine, int size, int32_t* __restrict__ owner) {
+  constexpr int SUB = (NPC == 3) ? 1 : 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= NT) return;
+  const int64_t cell = tid / SUB;
+  const int sub = (int)(tid % SUB);
+  const int s = seg_of(cell_off, ns, cell);
+  const int32_t local = (int32_t)((cell - cell_off[s]) * SUB + sub);
+  Tri t;
+  int32_t vid[3];
+  load_tri<NPC>(cell, sub, conn, xy, affine + 4 * s, t, vid);
+  const double mnx = fmin(t.X[0], fmin(t.X[1], t.X[2])), mxx = fmax(t.X[0], fmax(t.X[1], t.X[2]));
+  const double mny = fmin(t.Y[0], fmin(t.Y[1], t.Y[2])), mxy = fmax(t.Y[0], fmax(t.Y[1], t.Y[2]));
+  const double fi0 = fmax(ceil(__dsub_rn(mnx, 0.5)), 0.0), fi1 = fmin(floor(__dsub_rn(mxx, 0.5)), (double)(size - 1));
+  const double fj0 = fmax(ceil(__dsub_rn(mny, 0.5)), 0.0), fj1 = fmin(floor(__dsub_rn(mxy, 0.5)), (double)(size - 1));
+  if (!(fi1 >= fi0 && fj1 >= fj0)) return;
+  const int i0 = (int)fi0, i1 = (int)fi1, j0 = (int)fj0, j1 = (int)fj1;
+  int32_t* own = owner + (int64_t)s * size * size;
+  for (int j = j0; j <= j1; ++j) {
+    for (int i = i0; i <= i1; ++i) {
+      double w[3], a2;
+      bary(t, (double)i + 0.5, (double)j + 0.5, w, &a2);
+      if (w[0] >= 0.0 && w[1] >= 0.0 && w[2] >= 0.0 && a2 != 0.0) atomicMin(&own[j * size + i], local);
+    }
+  }
+}
+
+template <int NPC>
+__global__ void k_raster_shade(int ns, int size, const int64_t* __restrict__ cell_off,
+                               const int32_t* __restrict__ conn, const double* __restrict__ xy,
+                               const double* __restrict__ affine, const int32_t* __restrict__ owner,
+                               const double* __restrict__ u, const double* __restrict__ ranges,
+                               double value_scale, uint8_t* __restrict__ images) {
+  constexpr int SUB = (NPC == 3) ? 1 : 2;
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)size * size;
+  if (pix >= per * ns) return;
+  const int s = (int)(pix / per);
+  const int64_t lp = pix - (int64_t)s * per;
+  const int j = (int)(lp / size), i = (int)(lp - (int64_t)j * size);
+  const int32_t o = owner[pix];
+  uint8_t g0 = 255, g1 = 255;
+  if (o != 0x7fffffff) {
+    const int64_t cell = cell_off[s] + o / SUB;
+    Tri t;
+    int32_t vid[3];
+    load_tri<NPC>(cell, o % SUB, conn, xy, affine + 4 * s, t, vid);
+    double w[3], a2;
+    bary(t, (double)i + 0.5, (double)j + 0.5, w, &a2);
+    uint8_t g[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double s0 = __dmul_rn(value_scale, u[2 * (int64_t)vid[0] + c]);
+      const double s1 = __dmul_rn(value_scale, u[2 * (int64_t)vid[1] + c]);
+      const double s2 = __dmul_rn(value_scale, u[2 * (int64_t)vid[2] + c]);
+      const double val = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(w[0], s0), __dmul_rn(w[1], s1)), __dmul_rn(w[2], s2)), a2);
+      const double vmin = __dmul_rn(value_scale, ranges[4 * s + 2 * c]);
+      const double vmax = __dmul_rn(value_scale, ranges[4 * s + 2 * c + 1]);
+      const double rng = __dsub_rn(vmax, vmin);
+      double tt = 0.0;
+      if (rng > 0.0) tt = __ddiv_rn(__dsub_rn(val, vmin), rng);
+      tt = fmin(fmax(tt, 0.0), 1.0);
+      const double q = fmin(floor(__dmul_rn(256.0, tt)), 255.0);
+      g[c] = (uint8_t)(255.0 - q);
+    }
+    g0 = g[0];
+    g1 = g[1];
+  }
+  images[((int64_t)s * 2 + 0) * per + lp] = g0;
+  images[((int64_t)s * 2 + 1) * per + lp] = g1;
+}
+
+cudaError_t launch_raster(Batch& b, double value_scale) {
+  cudaStream_t st = b.ctx->stream;
+  const int T = 256;
+  const int64_t npix = (int64_t)b.ns * b.img_size * b.img_size;
+  if (npix == 0) return cudaSuccess;
+  k_owner_init<<<(unsigned)((npix + T - 1) / T), T, 0, st>>>(npix, b.owner);
+  const int64_t NT = b.NC * (b.npc == 3 ? 1 : 2);
+  if (NT) {
+    const unsigned g = (unsigned)((NT + T - 1) / T);
+    if (b.npc == 3) k_raster_cover<3><<<g, T, 0, st>>>(NT, b.d_cell_off, b.ns, b.conn, b.xy, b.affine, b.img_size, b.owner);
+    else k_raster_cover<4><<<g, T, 0, st>>>(NT, b.d_cell_off, b.ns, b.conn, b.xy, b.affine, b.img_size, b.owner);
+  }
+  const unsigned gp = (unsigned)((npix + T - 1) / T);
+  if (b.npc == 3)
+    k_raster_shade<3><<<gp, T, 0, st>>>(b.ns, b.img_size, b.d_cell_off, b.conn, b.xy, b.affine, b.owner, b.u, b.ranges,
+                                        value_scale, b.images);
+  else
+    k_raster_shade<4><<<gp, T, 0, st>>>(b.ns, b.img_size, b.d_cell_off, b.conn, b.xy, b.affine, b.owner, b.u, b.ranges,
+                                        value_scale, b.images);
+  return cudaGetLastError();
+}
+
+}  // namespace fea

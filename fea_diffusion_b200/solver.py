@@ -1,0 +1,256 @@
+"""Host-side objects over the C-ABI: samples, packed batches, contexts.
+
+A *sample* is one plate-condition: mesh + Dirichlet vertex mask + material cells + final-step
+load.  ``pack`` concatenates samples into the flat arrays ``fea_batch_desc`` expects; ``Context``
+owns a ``fea_ctx`` (one GPU, one stream); ``Batch`` wraps the staged life cycle
+create -> assemble -> solve -> rasterize -> download.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import BatchDesc, BatchInfo, FeaError, SolveStats, ptr
+
+
+@dataclass
+class Sample:
+    """Inputs of one plate-condition problem (what FEAnalysis.__init__ derives through sfepy,
+    reference datagen/fea_analysis.py:61-164)."""
+    coors: np.ndarray        # (n_v, 2) f64
+    conn: np.ndarray         # (n_cell, k) i32, as read from the mesh file
+    cell_region: np.ndarray  # (n_cell,) i8, -1 = no stiffness
+    D: np.ndarray            # (n_reg, 3, 3) f64
+    fixed: np.ndarray        # (n_v,) bool / u8
+    rhs: np.ndarray          # (n_v, 2) f64 final-step load (N_regions * sum of magnitudes)
+
+
+class PackedBatch:
+    """Concatenated, C-contiguous host arrays + the ctypes descriptor that points at them."""
+
+    def __init__(self, samples: Sequence[Sample]):
+        if not samples:
+            raise ValueError("empty batch")
+        k = samples[0].conn.shape[1]
+        if any(s.conn.shape[1] != k for s in samples):
+            raise ValueError("all samples of a batch must use the same cell type")
+        self.n = len(samples)
+        self.k = k
+        nv = np.array([len(s.coors) for s in samples], dtype=np.int64)
+        nc = np.array([len(s.conn) for s in samples], dtype=np.int64)
+        nr = np.array([len(s.D) for s in samples], dtype=np.int64)
+        self.vtx_off = np.concatenate([[0], np.cumsum(nv)]).astype(np.int64)
+        self.cell_off = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
+        self.reg_off = np.concatenate([[0], np.cumsum(nr)]).astype(np.int32)
+        cat = np.concatenate
+        self.xy = np.ascontiguousarray(cat([np.asarray(s.coors, dtype=np.float64).reshape(-1, 2) for s in samples]))
+        self.conn = np.ascontiguousarray(cat([np.asarray(s.conn, dtype=np.int32) for s in samples]))
+        self.cell_region = np.ascontiguousarray(cat([np.asarray(s.cell_region, dtype=np.int8) for s in samples]))
+        self.D = np.ascontiguousarray(cat([np.asarray(s.D, dtype=np.float64).reshape(-1, 3, 3) for s in samples]))
+        self.fixed = np.ascontiguousarray(cat([np.asarray(s.fixed).astype(np.uint8) for s in samples]))
+        self.rhs = np.ascontiguousarray(cat([np.asarray(s.rhs, dtype=np.float64).reshape(-1, 2) for s in samples]))
+        self.desc = BatchDesc(
+            n_samples=self.n, nodes_per_cell=k,
+            vtx_off=ptr(self.vtx_off), cell_off=ptr(self.cell_off), reg_off=ptr(self.reg_off),
+            xy=ptr(self.xy), conn=ptr(self.conn), cell_region=ptr(self.cell_region),
+            D=ptr(self.D), fixed=ptr(self.fixed), rhs=ptr(self.rhs))
+
+    @property
+    def n_vertices(self) -> int:
+        return int(self.vtx_off[-1])
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(sum(a.nbytes for a in (self.vtx_off, self.cell_off, self.reg_off, self.xy, self.conn,
+                                          self.cell_region, self.D, self.fixed, self.rhs)))
+
+    def split_vertices(self, a: np.ndarray) -> List[np.ndarray]:
+        return [a[self.vtx_off[s]:self.vtx_off[s + 1]] for s in range(self.n)]
+
+
+def pack(samples: Sequence[Sample]) -> PackedBatch:
+    return PackedBatch(samples)
+
+
+@dataclass
+class BatchResult:
+    u: np.ndarray          # (n_vertices, 2) final-step displacement
+    ranges: np.ndarray     # (n, 4): min ux, max ux, min uy, max uy (final step)
+    iters: np.ndarray
+    relres: np.ndarray
+    status: np.ndarray
+    images: Optional[np.ndarray] = None  # (n, 2, size, size) uint8
+    stats: Optional[dict] = None
+
+
+class Context:
+    """One fea_ctx: a GPU and a stream.  Not thread-safe; use one per host thread."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _capi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.fea_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FeaError(rc, "fea_ctx_create(device=%d) failed (no CUDA device?)" % device)
+        self.h = h
+        self.device = device
+        self._pinned = []
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise FeaError(rc, self.lib.fea_last_error(self.h).decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in self._pinned:
+                self.lib.fea_host_free(self.h, p)
+            self._pinned = []
+            self.lib.fea_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self.lib.fea_ctx_synchronize(self.h))
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over page-locked host memory (fea_host_alloc); released by close()."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        p = C.c_void_p()
+        self._check(self.lib.fea_host_alloc(self.h, count * dtype.itemsize, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_char * max(count * dtype.itemsize, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def create_batch(self, packed: PackedBatch) -> "Batch":
+        return Batch(self, packed)
+
+    def solve_batch(self, packed: PackedBatch, rtol: float = 1e-10, max_iter: int = 20000,
+                    image_size: int = 0, affine: Optional[np.ndarray] = None, value_scale: float = 1.0,
+                    out: Optional[BatchResult] = None) -> BatchResult:
+        """One-call host-buffer path (fea_solve_batch): H2D, assemble, solve, rasterise, D2H."""
+        n, nv = packed.n, packed.n_vertices
+        if out is None:
+            out = BatchResult(u=np.empty((nv, 2)), ranges=np.empty((n, 4)), iters=np.empty(n, np.int32),
+                              relres=np.empty(n), status=np.empty(n, np.int32))
+        if image_size > 0:
+            affine = np.ascontiguousarray(affine, dtype=np.float64).reshape(n, 4)
+            if out.images is None or out.images.shape != (n, 2, image_size, image_size):
+                out.images = np.empty((n, 2, image_size, image_size), np.uint8)
+        st = SolveStats()
+        self._check(self.lib.fea_solve_batch(
+            self.h, C.byref(packed.desc), float(rtol), int(max_iter), int(image_size), ptr(affine),
+            float(value_scale), ptr(out.u), ptr(out.ranges), ptr(out.iters), ptr(out.relres), ptr(out.status),
+            ptr(out.images) if image_size > 0 else None, C.byref(st)))
+        out.stats = st.as_dict()
+        return out
+
+
+class Batch:
+    """Staged life cycle of one device-resident batch."""
+
+    def __init__(self, ctx: Context, packed: PackedBatch):
+        self.ctx, self.packed = ctx, packed
+        h = C.c_void_p()
+        ctx._check(ctx.lib.fea_batch_create(ctx.h, C.byref(packed.desc), C.byref(h)))
+        self.h = h
+        self.image_size = 0
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.fea_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.destroy()
+
+    def assemble(self):
+        self.ctx._check(self.ctx.lib.fea_batch_assemble(self.h))
+        return self
+
+    def solve(self, rtol: float = 1e-10, max_iter: int = 20000):
+        self.ctx._check(self.ctx.lib.fea_batch_solve(self.h, float(rtol), int(max_iter)))
+        return self
+
+    def rasterize(self, size: int, affine: np.ndarray, value_scale: float = 1.0):
+        affine = np.ascontiguousarray(affine, dtype=np.float64).reshape(self.packed.n, 4)
+        self.ctx._check(self.ctx.lib.fea_batch_rasterize(self.h, int(size), ptr(affine), float(value_scale)))
+        self.image_size = size
+        return self
+
+    def download(self, images: bool = False) -> BatchResult:
+        n, nv = self.packed.n, self.packed.n_vertices
+        r = BatchResult(u=np.empty((nv, 2)), ranges=np.empty((n, 4)), iters=np.empty(n, np.int32),
+                        relres=np.empty(n), status=np.empty(n, np.int32))
+        self.ctx._check(self.ctx.lib.fea_batch_download(self.h, ptr(r.u), ptr(r.ranges), ptr(r.iters),
+                                                        ptr(r.relres), ptr(r.status)))
+        if images:
+            r.images = np.empty((n, 2, self.image_size, self.image_size), np.uint8)
+            self.ctx._check(self.ctx.lib.fea_batch_download_images(self.h, ptr(r.images)))
+        r.stats = self.stats()
+        return r
+
+    def info(self) -> dict:
+        i = BatchInfo()
+        self.ctx._check(self.ctx.lib.fea_batch_get_info(self.h, C.byref(i)))
+        return i.as_dict()
+
+    def stats(self) -> dict:
+        s = SolveStats()
+        self.ctx._check(self.ctx.lib.fea_batch_get_solve_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def sample_sizes(self):
+        n = self.packed.n
+        a, z = np.empty(n, np.int64), np.empty(n, np.int64)
+        self.ctx._check(self.ctx.lib.fea_batch_sample_sizes(self.h, ptr(a), ptr(z)))
+        return a, z
+
+    def conn(self):
+        c = np.empty_like(self.packed.conn)
+        f = np.empty(self.packed.n, np.int32)
+        self.ctx._check(self.ctx.lib.fea_batch_get_conn(self.h, ptr(c), ptr(f)))
+        return c, f
+
+    def element_stiffness(self) -> np.ndarray:
+        k = self.packed.k
+        ke = np.empty((len(self.packed.conn), 2 * k, 2 * k))
+        self.ctx._check(self.ctx.lib.fea_batch_get_element_stiffness(self.h, ptr(ke)))
+        return ke
+
+    def csr(self, sample: int, values: bool = True):
+        """scipy CSR of one sample's reduced stiffness matrix in sfepy's layout."""
+        import scipy.sparse as sp
+        a, z = self.sample_sizes()
+        n, nnz = int(a[sample]), int(z[sample])
+        indptr = np.empty(n + 1, np.int32)
+        indices = np.empty(nnz, np.int32)
+        data = np.empty(nnz) if values else None
+        self.ctx._check(self.ctx.lib.fea_batch_get_csr(self.h, int(sample), ptr(indptr), ptr(indices), ptr(data)))
+        if data is None:
+            data = np.ones(nnz)
+        return sp.csr_matrix((data, indices, indptr), shape=(n, n))
+
+    def spmv(self, sample: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self.ctx._check(self.ctx.lib.fea_batch_spmv(self.h, int(sample), ptr(x), ptr(y)))
+        return y

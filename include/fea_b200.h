@@ -1,0 +1,171 @@
+/*
+ * fea_b200.h -- C-ABI of libfea_b200.so: the B200-native replacement for the FEA
+ * data-synthesis hot path of namanxkumar/fea-diffusion.
+ *
+ * The reference has no FFI; its boundary is the Python class
+ * datagen.fea_analysis.FEAnalysis (reference datagen/fea_analysis.py:31-613) whose
+ * arithmetic runs inside sfepy 2023.3 / scipy SuperLU / VTK.  Each entry point below
+ * names the reference lines whose work it replaces.  All functions are extern "C",
+ * take plain pointers and sizes, never throw, and return a fea_status (0 = OK);
+ * fea_last_error(ctx) gives the message of the last failure on that context.
+ *
+ * Data model: a *batch* is a set of independent plate-condition samples
+ * (one mesh + one constraint/force/material condition each) that are assembled and
+ * solved together, lock-step, as one block-diagonal system.  Host arrays are the
+ * concatenation over samples with offset tables (C-contiguous fp64/int32/uint8).
+ * The caller owns every host buffer; the library owns device memory behind the
+ * opaque handles.  One fea_ctx per (host thread, GPU); a ctx owns one CUDA stream.
+ *
+ * Units: vertex v of a sample has DOFs 2v (x) and 2v+1 (y) (sfepy field 'fu',
+ * fea_analysis.py:66).
+ */
+#ifndef FEA_B200_H
+#define FEA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEA_VERSION_MAJOR 0
+#define FEA_VERSION_MINOR 1
+
+typedef struct fea_ctx fea_ctx;
+typedef struct fea_batch fea_batch;
+
+/* return codes of every entry point */
+enum fea_status {
+  FEA_OK = 0,
+  FEA_BAD_ARG = 1,
+  FEA_CUDA_ERROR = 2,
+  FEA_OUT_OF_MEMORY = 3,
+  FEA_BAD_STATE = 4,      /* call order violated (e.g. solve before assemble) */
+  FEA_MESH_ERROR = 5      /* vertex valence above the supported maximum, bad index */
+};
+
+/* per-sample solver outcome (fea_batch_download: status[]) */
+enum fea_sample_status {
+  FEA_SAMPLE_NOT_RUN = -1,
+  FEA_SAMPLE_CONVERGED = 0,
+  FEA_SAMPLE_MAX_ITER = 1,   /* not converged within max_iter */
+  FEA_SAMPLE_BREAKDOWN = 2,  /* p^T A p <= 0 or non-finite: matrix not SPD (floating region, F4) */
+  FEA_SAMPLE_EMPTY_ROW = 3   /* an active vertex touches no stiffness cell: exactly singular
+                                (the reference's SuperLU-NaN -> calculate() False path, A-18) */
+};
+
+/*
+ * Concatenated description of n_samples plate-condition problems.
+ * Replaces the state FEAnalysis.__init__ builds through sfepy
+ * (fea_analysis.py:61-164): mesh, Dirichlet set, material cells, load.
+ */
+typedef struct fea_batch_desc {
+  int32_t n_samples;
+  int32_t nodes_per_cell;       /* 3 = P1 triangles, 4 = Q1 quads (uniform over the batch) */
+  const int64_t* vtx_off;       /* [n_samples+1] vertex offsets */
+  const int64_t* cell_off;      /* [n_samples+1] cell offsets */
+  const int32_t* reg_off;       /* [n_samples+1] material-table offsets */
+  const double*  xy;            /* [vtx_off[n]*2] vertex coordinates (fea_analysis.py:61) */
+  const int32_t* conn;          /* [cell_off[n]*nodes_per_cell] sample-local vertex ids, as read
+                                   from the mesh file; orientation is fixed on device (A-2) */
+  const int8_t*  cell_region;   /* [cell_off[n]] sample-local material index, or -1 for cells that
+                                   carry no stiffness (seam cells, F4; fea_analysis.py:235-252) */
+  const double*  D;             /* [reg_off[n]*9] row-major 3x3 elasticity matrices,
+                                   strain order (e11, e22, 2e12) (fea_analysis.py:257-266) */
+  const uint8_t* fixed;         /* [vtx_off[n]] 1 = both DOFs of the vertex are Dirichlet-zero
+                                   (EssentialBC 'u.all': 0, fea_analysis.py:362-369) */
+  const double*  rhs;           /* [vtx_off[n]*2] full-DOF load of the final step (t = 1):
+                                   N_regions * sum of point-load magnitudes (F2/F3,
+                                   fea_analysis.py:313-359) */
+} fea_batch_desc;
+
+typedef struct fea_batch_info {
+  int64_t n_vertices;       /* total vertices */
+  int64_t n_cells;
+  int64_t n_active_dofs;    /* sum of reduced system sizes */
+  int64_t nnz;              /* sum of reduced scalar CSR non-zeros (sfepy pattern, A-11) */
+  int64_t block_rows;       /* padded 2x2 block rows of the lock-step system */
+  int64_t sell_blocks;      /* stored 2x2 blocks incl. slice padding */
+  int32_t n_flipped;        /* cells whose orientation was corrected (A-2) */
+  int32_t max_row_blocks;   /* longest block row */
+} fea_batch_info;
+
+typedef struct fea_solve_stats {
+  int32_t iterations;       /* lock-step iterations executed (max over samples) */
+  int32_t n_converged;
+  int32_t spmv_launches_timed;
+  int32_t update_launches_timed;
+  float   spmv_ms_avg;      /* CUDA-event average duration of the SpMV kernel launch */
+  float   update_ms_avg;    /* same for the fused vector-update kernel */
+  float   solve_ms;         /* whole PCG loop, CUDA events on the ctx stream */
+  int64_t kernel_launches;  /* kernels launched by this solve */
+} fea_solve_stats;
+
+/* ---- library / context -------------------------------------------------- */
+int  fea_version(int* major, int* minor);
+int  fea_ctx_create(int device, fea_ctx** out);
+int  fea_ctx_destroy(fea_ctx* ctx);
+const char* fea_last_error(const fea_ctx* ctx);
+/* pinned host memory for zero-staging uploads/downloads (optional) */
+int  fea_host_alloc(fea_ctx* ctx, size_t bytes, void** out);
+int  fea_host_free(fea_ctx* ctx, void* p);
+int  fea_ctx_synchronize(fea_ctx* ctx);
+
+/* ---- batch life cycle ---------------------------------------------------
+ * create   : H2D of the description; cell orientation fix (A-2); Dirichlet
+ *            equation map (problem.set_bcs, fea_analysis.py:422; A-9).
+ * assemble : element stiffness (dw_lin_elastic, fea_analysis.py:153-160,302-310; A-4/A-5),
+ *            matrix graph (sfepy mesh_graph inside problem.solve, :437; A-11),
+ *            value assembly with Dirichlet rows/cols dropped (A-10), Jacobi scaling,
+ *            load vector (dw_point_load, :338-344).
+ * solve    : Jacobi-preconditioned fp64 CG for all samples lock-step; replaces
+ *            Newton + ScipyDirect + SimpleTimeSteppingSolver (:371-375, 425-439):
+ *            one solve at t = 1, load steps are t_k multiples of it (F5).
+ *            Also produces per-sample (min,max) of both components (ranges.txt, A-17).
+ * rasterize: displacement_x / displacement_y gray images of step 1
+ *            (save_output_images, :526-613; custom_plotter.py:121-193; A-16).
+ */
+int  fea_batch_create(fea_ctx* ctx, const fea_batch_desc* desc, fea_batch** out);
+int  fea_batch_assemble(fea_batch* b);
+int  fea_batch_solve(fea_batch* b, double rtol, int32_t max_iter);
+/* affine[4*s..] = (ax, bx, ay, by): pixel = a*world + b; value_scale = t_1 (images are of
+ * step 1); images are [n_samples][2][size][size] uint8, background 255. */
+int  fea_batch_rasterize(fea_batch* b, int32_t size, const double* affine, double value_scale);
+int  fea_batch_destroy(fea_batch* b);
+
+/* ---- results (host buffers, may be NULL to skip) ------------------------- */
+/* u [n_vertices*2] final-step displacement, zeros at fixed DOFs (A-15), NaN for EMPTY_ROW
+ * samples; ranges [n_samples*4] = (min ux, max ux, min uy, max uy) of the final step;
+ * iters/status [n_samples]; relres [n_samples] = sqrt(r.z / r0.z0) at exit. */
+int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
+                        double* relres, int32_t* status);
+int  fea_batch_download_images(fea_batch* b, uint8_t* images);
+int  fea_batch_get_info(fea_batch* b, fea_batch_info* out);
+int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
+
+/* ---- inspection entry points used by the parity tests -------------------- */
+/* per-sample reduced sizes: n_active_dofs[s], nnz[s] (scalar CSR) */
+int  fea_batch_sample_sizes(fea_batch* b, int64_t* n_active_dofs, int64_t* nnz);
+/* orientation-fixed connectivity (sample-local ids) and per-sample flip counts */
+int  fea_batch_get_conn(fea_batch* b, int32_t* conn, int32_t* n_flipped);
+/* element matrices [n_cells][2k][2k], local dof = 2*node + comp; zero for region -1 cells */
+int  fea_batch_get_element_stiffness(fea_batch* b, double* ke);
+/* reduced scalar CSR of one sample in sfepy's layout (A-11): indptr [n+1], indices [nnz],
+ * data [nnz] = UNSCALED stiffness values; any pointer may be NULL */
+int  fea_batch_get_csr(fea_batch* b, int32_t sample, int32_t* indptr, int32_t* indices,
+                       double* data);
+/* y = K x for one sample through the product SpMV kernel (x, y over active DOFs, unscaled) */
+int  fea_batch_spmv(fea_batch* b, int32_t sample, const double* x, double* y);
+
+/* ---- one-call convenience: create + assemble + solve (+ rasterize) + download + destroy.
+ * This is the host-buffer end-to-end path (the "e2e" number of bench.py). */
+int  fea_solve_batch(fea_ctx* ctx, const fea_batch_desc* desc, double rtol, int32_t max_iter,
+                     int32_t image_size, const double* affine, double value_scale,
+                     double* u, double* ranges, int32_t* iters, double* relres, int32_t* status,
+                     uint8_t* images, fea_solve_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEA_B200_H */

@@ -291,17 +291,27 @@ class OracleProblem:
         return int((np.sum(self.cell_regions_all, axis=0) > 1).sum())
 
     def stiffness(self) -> sp.csr_matrix:
+        """Sum over the LHS terms (one per material region, complete cells only), assembled as
+        one COO so that explicit zeros survive (A-11) -- sparse '+' would prune them."""
         n_v = len(self.coors)
-        A = None
+        eq, n = equation_map(self.fixed_vertex)
+        k = self.conn.shape[1]
+        R, Cc, V = [], [], []
         for i, cm in enumerate(self.cell_regions_all):
-            creg = np.where(cm, 0, -1)
-            Ke = element_stiffness(self.coors, self.conn, self.D[i])
-            Ai = assemble_csr(n_v, self.conn, Ke, creg, self.fixed_vertex)
-            A = Ai if A is None else A + Ai
-        if A is None:
-            _, n = equation_map(self.fixed_vertex)
-            A = sp.csr_matrix((n, n))
-        A = sp.csr_matrix(A)
+            c = self.conn[cm]
+            if not len(c):
+                continue
+            ke = element_stiffness(self.coors, c, self.D[i])
+            dofs = (2 * c[:, :, None] + np.arange(2)[None, None, :]).reshape(len(c), 2 * k)
+            e = eq[dofs]
+            R.append(np.repeat(e[:, :, None], 2 * k, axis=2).ravel())
+            Cc.append(np.repeat(e[:, None, :], 2 * k, axis=1).ravel())
+            V.append(ke.reshape(-1))
+        if not R:
+            return sp.csr_matrix((n, n))
+        rows, cols, vals = np.concatenate(R), np.concatenate(Cc), np.concatenate(V)
+        ok = (rows >= 0) & (cols >= 0)
+        A = sp.coo_matrix((vals[ok], (rows[ok], cols[ok])), shape=(n, n)).tocsr()
         A.sort_indices()
         return A
 
