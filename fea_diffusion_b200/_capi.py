@@ -17,9 +17,11 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 # every symbol include/fea_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "fea_version", "fea_ctx_create", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
-    "fea_host_free", "fea_ctx_synchronize", "fea_batch_create", "fea_batch_assemble",
+    "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
+    "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
     "fea_batch_download_images", "fea_batch_get_info", "fea_batch_get_solve_stats",
+    "fea_batch_get_timed_launches",
     "fea_batch_sample_sizes", "fea_batch_get_conn", "fea_batch_get_element_stiffness",
     "fea_batch_get_csr", "fea_batch_spmv", "fea_solve_batch",
 ]
@@ -88,6 +90,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
         "fea_host_free": (C.c_int, [P, P]),
         "fea_ctx_synchronize": (C.c_int, [P]),
+        "fea_ctx_event_record": (C.c_int, [P, I32]),
+        "fea_ctx_event_elapsed_ms": (C.c_int, [P, I32, I32, P]),
+        "fea_ctx_kernel_launches": (C.c_int, [P, P]),
         "fea_batch_create": (C.c_int, [P, C.POINTER(BatchDesc), C.POINTER(P)]),
         "fea_batch_assemble": (C.c_int, [P]),
         "fea_batch_solve": (C.c_int, [P, F64, I32]),
@@ -97,6 +102,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_download_images": (C.c_int, [P, P]),
         "fea_batch_get_info": (C.c_int, [P, C.POINTER(BatchInfo)]),
         "fea_batch_get_solve_stats": (C.c_int, [P, C.POINTER(SolveStats)]),
+        "fea_batch_get_timed_launches": (C.c_int, [P, I32, P, P, P]),
         "fea_batch_sample_sizes": (C.c_int, [P, P, P]),
         "fea_batch_get_conn": (C.c_int, [P, P, P]),
         "fea_batch_get_element_stiffness": (C.c_int, [P, P]),

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -16,6 +17,7 @@ struct fea_ctx {
   std::vector<cudaEvent_t> events;
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_user[8] = {};
 };
 struct fea_batch {
   Batch b;
@@ -100,6 +102,7 @@ int fea_ctx_create(int device, fea_ctx** out) {
   if (e != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
   if ((e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
   cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("FEA_SPMV_VARIANT")) ctx->c.spmv_variant = atoi(v);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -114,6 +117,7 @@ int fea_ctx_create(int device, fea_ctx** out) {
   cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev_t0);
   cudaEventCreate(&ctx->ev_t1);
+  for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
   ctx->events.resize(3 * kMaxTimed);
   for (auto& ev : ctx->events) cudaEventCreate(&ev);
   *out = ctx;
@@ -129,6 +133,7 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaEventDestroy(ctx->ev_poll[1]);
   cudaEventDestroy(ctx->ev_t0);
   cudaEventDestroy(ctx->ev_t1);
+  for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
   cudaFreeHost(ctx->h_flag);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
@@ -151,6 +156,25 @@ int fea_host_free(fea_ctx* ctx, void* p) {
 int fea_ctx_synchronize(fea_ctx* ctx) {
   if (!ctx) return FEA_BAD_ARG;
   CK(ctx, cudaStreamSynchronize(ctx->c.stream));
+  return FEA_OK;
+}
+
+int fea_ctx_event_record(fea_ctx* ctx, int32_t slot) {
+  if (!ctx || slot < 0 || slot >= 8) return FEA_BAD_ARG;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaEventRecord(ctx->ev_user[slot], ctx->c.stream));
+  return FEA_OK;
+}
+int fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t a, int32_t b, float* ms) {
+  if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return FEA_BAD_ARG;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaEventSynchronize(ctx->ev_user[b]));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev_user[a], ctx->ev_user[b]));
+  return FEA_OK;
+}
+int fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out) {
+  if (!ctx || !out) return FEA_BAD_ARG;
+  *out = ctx->c.launches;
   return FEA_OK;
 }
 
@@ -186,7 +210,9 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   b.NBR = 0;
   for (int s = 0; s < ns; ++s) {
     const int64_t nv = b.vtx_off[s + 1] - b.vtx_off[s];
-    b.NBR += (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
+    const int64_t pad = (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
+    b.NBR += pad;
+    b.max_cta_count = std::max<int32_t>(b.max_cta_count, (int32_t)(pad / kCtaRows));  // upper bound
   }
   cudaStream_t st = ctx->c.stream;
   int32_t* conn_local = nullptr;
@@ -230,6 +256,7 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(cudaMemsetAsync(b.empty, 0, sizeof(int32_t) * ns, st));
   A(cudaMemsetAsync(b.vertex_of_row, 0xFF, sizeof(int32_t) * std::max<int64_t>(1, b.NBR), st));
   A(launch_setup(b, creg_local, conn_local));
+  ctx->c.launches += 6;
   if (conn_local) cudaFreeAsync(conn_local, st);
   if (creg_local) cudaFreeAsync(creg_local, st);
 #undef A
@@ -283,6 +310,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.val, b.n_blocks * 2));
   CK(ctx, dalloc(b, &b.col, b.n_blocks));
   CK(ctx, dalloc(b, &b.dscale, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.dcoup, b.NBR));
   CK(ctx, dalloc(b, &b.x, b.NBR * 2));
   CK(ctx, dalloc(b, &b.r, b.NBR * 2));
   CK(ctx, dalloc(b, &b.p0, b.NBR * 2));
@@ -299,8 +327,8 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.sc.done, b.ns));
   CK(ctx, dalloc(b, &b.sc.iters, b.ns));
   CK(ctx, dalloc(b, &b.sc.status, b.ns));
-  CK(ctx, dalloc(b, &b.sc.cntA, b.ns));
-  CK(ctx, dalloc(b, &b.sc.cntB, b.ns));
+  CK(ctx, dalloc(b, &b.sc.psumA, b.ns));
+  CK(ctx, dalloc(b, &b.sc.psumB, b.ns));
   CK(ctx, dalloc(b, &b.sc.n_done, 1));
   CK(ctx, dalloc(b, &b.rz_last, b.ns));
   CK(ctx, dalloc(b, &b.relres, b.ns));
@@ -310,6 +338,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, cudaMemsetAsync(b.sc.iters, 0, sizeof(int32_t) * b.ns, st));
   CK(ctx, cudaMemsetAsync(b.relres, 0, sizeof(double) * b.ns, st));
   CK(ctx, launch_sell_fill(b));
+  ctx->c.launches += 1 + 10 + 4 + 1 + 2;
   b.assembled = true;
   return FEA_OK;
 }
@@ -326,19 +355,19 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
   int64_t launches = 0;
   CK(ctx, cudaEventRecord(ctx->ev_t0, st));
   CK(ctx, launch_pcg_init(b, rtol));
-  launches += 1;
+  launches += 2;
   // capture kChunk-2 iterations once; the first two iterations of every chunk are plain
   // launches so that one spmv/update pair per chunk can be bracketed by timing events
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   CK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   for (int i = 2; i < kChunk; ++i) {
-    launch_pcg_spmv(b, i & 1, st);
-    launch_pcg_update(b, i & 1, max_iter, st);
+    launch_pcg_spmv(b, i & 1, max_iter, st);
+    launch_pcg_update(b, i & 1, st);
   }
   CK(ctx, cudaStreamEndCapture(st, &graph));
   CK(ctx, cudaGraphInstantiate(&exec, graph, 0));
-  const int max_chunks = (max_iter + kChunk - 1) / kChunk + 1;
+  const int max_chunks = (max_iter + kChunk - 1) / kChunk + 2;
   std::vector<int> done_after;  // n_done observed after chunk k
   int timed = 0;
   int k = 0;
@@ -346,20 +375,20 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
   for (; k < max_chunks; ++k) {
     if (timed < kMaxTimed) {
       cudaEventRecord(ctx->events[3 * timed], st);
-      launch_pcg_spmv(b, 0, st);
+      launch_pcg_spmv(b, 0, max_iter, st);
       cudaEventRecord(ctx->events[3 * timed + 1], st);
-      launch_pcg_update(b, 0, max_iter, st);
+      launch_pcg_update(b, 0, st);
       cudaEventRecord(ctx->events[3 * timed + 2], st);
       ++timed;
     } else {
-      launch_pcg_spmv(b, 0, st);
-      launch_pcg_update(b, 0, max_iter, st);
+      launch_pcg_spmv(b, 0, max_iter, st);
+      launch_pcg_update(b, 0, st);
     }
-    launch_pcg_spmv(b, 1, st);
-    launch_pcg_update(b, 1, max_iter, st);
+    launch_pcg_spmv(b, 1, max_iter, st);
+    launch_pcg_update(b, 1, st);
     e = cudaGraphLaunch(exec, st);
     if (e != cudaSuccess) break;
-    launches += 2 * kChunk;
+    launches += (int64_t)pcg_launches_per_iteration(b) * kChunk;
     cudaMemcpyAsync(&b.h_flag[k & 1], b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(ctx->ev_poll[k & 1], st);
     if (k >= 1) {
@@ -385,8 +414,15 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
   // average only over timed launches that ran with every system still active
   double sa = 0, su = 0;
   int na = 0;
+  b.t_spmv.assign(timed, 0.f);
+  b.t_update.assign(timed, 0.f);
   for (int t = 0; t < timed; ++t) {
-    const bool all_active = (t == 0) || (t - 1 < (int)done_after.size() && done_after[t - 1] == 0);
+    cudaEventElapsedTime(&b.t_spmv[t], ctx->events[3 * t], ctx->events[3 * t + 1]);
+    cudaEventElapsedTime(&b.t_update[t], ctx->events[3 * t + 1], ctx->events[3 * t + 2]);
+  }
+  for (int t = 0; t < timed; ++t) {
+    // (a few systems may finish at once, e.g. loads that fall on constrained vertices)
+    const bool all_active = (t == 0) || (t - 1 < (int)done_after.size() && done_after[t - 1] * 20 <= b.ns);
     if (!all_active) break;
     float a = 0, u = 0;
     cudaEventElapsedTime(&a, ctx->events[3 * t], ctx->events[3 * t + 1]);
@@ -395,12 +431,18 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
     su += u;
     ++na;
   }
+  if (getenv("FEA_DEBUG")) {
+    fprintf(stderr, "[fea] solve: chunks=%d timed=%d na=%d done_after:", k, timed, na);
+    for (size_t i = 0; i < done_after.size() && i < 24; ++i) fprintf(stderr, " %d", done_after[i]);
+    fprintf(stderr, "\n");
+  }
   b.stats.spmv_launches_timed = na;
   b.stats.update_launches_timed = na;
   b.stats.spmv_ms_avg = na ? (float)(sa / na) : 0.f;
   b.stats.update_ms_avg = na ? (float)(su / na) : 0.f;
   cudaEventElapsedTime(&b.stats.solve_ms, ctx->ev_t0, ctx->ev_t1);
   b.stats.kernel_launches = launches;
+  ctx->c.launches += launches;
   b.solved = true;
   return FEA_OK;
 }
@@ -422,6 +464,7 @@ int fea_batch_rasterize(fea_batch* hb, int32_t size, const double* affine, doubl
   }
   CK(ctx, cudaMemcpyAsync(b.affine, affine, sizeof(double) * 4 * b.ns, cudaMemcpyHostToDevice, st));
   CK(ctx, launch_raster(b, value_scale));
+  ctx->c.launches += 3;
   b.rasterized = true;
   return FEA_OK;
 }
@@ -504,6 +547,18 @@ int fea_batch_get_info(fea_batch* hb, fea_batch_info* out) {
 int fea_batch_get_solve_stats(fea_batch* hb, fea_solve_stats* out) {
   if (!hb || !out) return FEA_BAD_ARG;
   *out = hb->b.stats;
+  return FEA_OK;
+}
+
+int fea_batch_get_timed_launches(fea_batch* hb, int32_t cap, float* spmv_ms, float* update_ms, int32_t* n_out) {
+  if (!hb || !n_out || cap < 0) return FEA_BAD_ARG;
+  const Batch& b = hb->b;
+  const int n = (int)b.t_spmv.size();
+  *n_out = n;
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (spmv_ms) spmv_ms[i] = b.t_spmv[i];
+    if (update_ms) update_ms[i] = b.t_update[i];
+  }
   return FEA_OK;
 }
 

@@ -21,6 +21,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int sm_count = 148;
+  int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
+  int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };
 
 // Per-system (sample) solver scalars, structure of arrays on device.
@@ -32,8 +34,8 @@ struct SysScalars {
   int32_t* done;     // 0 = iterating, 1 = finished
   int32_t* iters;
   int32_t* status;
-  unsigned int* cntA;  // arrival counters of the last-block reductions
-  unsigned int* cntB;
+  double* psumA;     // per-system sums of the CTA partials (two-level mode, huge systems only)
+  double* psumB;
   int32_t* n_done;   // single counter: finished systems
 };
 
@@ -69,6 +71,7 @@ struct Batch {
   int32_t* sys_of_cta = nullptr;     // [NBR/kCtaRows]
   int32_t* cta_first = nullptr;      // [ns] first CTA of the system
   int32_t* cta_count = nullptr;      // [ns]
+  int32_t max_cta_count = 0;         // host copy: most CTAs any one system owns
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending
@@ -86,6 +89,7 @@ struct Batch {
   double2* val = nullptr;        // [n_blocks*2]  per (slice,j): 32 top rows then 32 bottom rows
   int32_t* col = nullptr;        // [n_blocks]
   double* dscale = nullptr;      // [NBR*2] 1/sqrt(diag)
+  double* dcoup = nullptr;       // [NBR] scaled x-y coupling of the diagonal block
   int32_t max_row_blocks = 0;
   // solver vectors [NBR*2]
   double *x = nullptr, *r = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr;
@@ -102,6 +106,7 @@ struct Batch {
   int32_t* owner = nullptr;  // [ns*size*size]
   double* affine = nullptr;  // [ns*4]
   fea_solve_stats stats{};
+  std::vector<float> t_spmv, t_update;  // per timed launch (one per chunk)
   // pinned host scratch
   int32_t* h_flag = nullptr;
 };
@@ -117,8 +122,9 @@ cudaError_t launch_sell_fill(Batch& b);                       // dscale, val, co
 cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d_indices,
                               double* d_data);
 cudaError_t launch_pcg_init(Batch& b, double rtol);
-cudaError_t launch_pcg_spmv(Batch& b, int parity, cudaStream_t st);
-cudaError_t launch_pcg_update(Batch& b, int parity, int max_iter, cudaStream_t st);
+cudaError_t launch_pcg_spmv(Batch& b, int parity, int max_iter, cudaStream_t st);
+cudaError_t launch_pcg_update(Batch& b, int parity, cudaStream_t st);
+int pcg_launches_per_iteration(const Batch& b);
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);
@@ -148,12 +154,12 @@ __device__ __forceinline__ int warp_max_i(int v) {
 // streaming 16-byte load that does not allocate in L1 (matrix values, read once per kernel)
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
   double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ int ld_stream_i32(const int* p) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 // binary search: largest s with off[s] <= i   (off has n+1 entries, off[0] = 0)

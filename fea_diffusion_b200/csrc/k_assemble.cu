@@ -10,6 +10,9 @@
 //   col[e] = block column (global block row id of the neighbour vertex)
 // so a warp reads 512 contiguous bytes per load instruction.  Values are stored scaled:
 //   Khat = S K S,  S = diag(1/sqrt(K_ii))  ->  CG on Khat == Jacobi-PCG on K.
+// Only OFF-diagonal blocks live in the SELL arrays.  After scaling the diagonal block of a
+// vertex is [[1, a], [a, 1]] (unit diagonal up to one rounding of s*K_ii*s, taken as exactly 1),
+// so it is kept as the single coupling a in dcoup[row]: 8 bytes instead of a 36-byte entry.
 // Row sums run over the vertex's incident cells in ascending cell order: atomic-free,
 // bitwise reproducible.
 #include "fea_internal.cuh"
@@ -22,7 +25,7 @@ __global__ void k_slice_len(int n_slices, const int32_t* __restrict__ vertex_of_
   const int slice = (int)(row >> 5);
   if (slice >= n_slices) return;
   const int v = vertex_of_row[row];
-  int len = v >= 0 ? adj_ptr[v + 1] - adj_ptr[v] : 0;
+  int len = v >= 0 ? max(adj_ptr[v + 1] - adj_ptr[v] - 1, 0) : 0;  // off-diagonal blocks only
   len = warp_max_i(len);
   if ((threadIdx.x & 31) == 0) slice_len[slice] = len;
 }
@@ -102,7 +105,7 @@ __global__ void k_sell_fill(int64_t NBR, const int32_t* __restrict__ vertex_of_r
                             const int32_t* __restrict__ inc, const int32_t* __restrict__ conn,
                             const double* __restrict__ ke, const double* __restrict__ dscale,
                             const int32_t* __restrict__ slice_len, const int64_t* __restrict__ slice_ptr,
-                            double2* __restrict__ val, int32_t* __restrict__ col) {
+                            double2* __restrict__ val, int32_t* __restrict__ col, double* __restrict__ dcoup) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= NBR) return;
   const int lane = threadIdx.x & 31;
@@ -118,24 +121,31 @@ __global__ void k_sell_fill(int64_t NBR, const int32_t* __restrict__ vertex_of_r
     s0 = dscale[2 * row];
     s1 = dscale[2 * row + 1];
   }
-  for (int j = 0; j < L; ++j) {
-    double2 top = make_double2(0.0, 0.0), bot = make_double2(0.0, 0.0);
-    int c = (int)row;
-    if (j < n) {
-      const int w = adj[a0 + j];
-      const int wr = row_of_vertex[w];
-      double k[4];
-      block_of_pair<NPC>(v, w, inc_ptr, inc, conn, ke, k);
-      const double t0 = dscale[2 * (int64_t)wr], t1 = dscale[2 * (int64_t)wr + 1];
-      top = make_double2(s0 * k[0] * t0, s0 * k[1] * t1);
-      bot = make_double2(s1 * k[2] * t0, s1 * k[3] * t1);
-      c = wr;
+  double coup = 0.0;
+  int j = 0;
+  for (int i = 0; i < n; ++i) {
+    const int w = adj[a0 + i];
+    double k[4];
+    block_of_pair<NPC>(v, w, inc_ptr, inc, conn, ke, k);
+    if (w == v) {
+      coup = s0 * k[1] * s1;
+      continue;
     }
+    const int wr = row_of_vertex[w];
+    const double t0 = dscale[2 * (int64_t)wr], t1 = dscale[2 * (int64_t)wr + 1];
     const int64_t e = base + (int64_t)j * 32;
-    val[2 * e + lane] = top;
-    val[2 * e + 32 + lane] = bot;
-    col[e + lane] = c;
+    val[2 * e + lane] = make_double2(s0 * k[0] * t0, s0 * k[1] * t1);
+    val[2 * e + 32 + lane] = make_double2(s1 * k[2] * t0, s1 * k[3] * t1);
+    col[e + lane] = wr;
+    ++j;
   }
+  for (; j < L; ++j) {  // slice padding: zero block pointing at the own row
+    const int64_t e = base + (int64_t)j * 32;
+    val[2 * e + lane] = make_double2(0.0, 0.0);
+    val[2 * e + 32 + lane] = make_double2(0.0, 0.0);
+    col[e + lane] = (int32_t)row;
+  }
+  dcoup[row] = coup;
 }
 
 cudaError_t launch_sell_fill(Batch& b) {
@@ -146,11 +156,11 @@ cudaError_t launch_sell_fill(Batch& b) {
   if (b.npc == 3) {
     k_diag_scale<3><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vsample, b.inc_ptr, b.inc, b.ke, b.dscale, b.empty);
     k_sell_fill<3><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.row_of_vertex, b.adj_ptr, b.adj, b.inc_ptr, b.inc,
-                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col);
+                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col, b.dcoup);
   } else {
     k_diag_scale<4><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vsample, b.inc_ptr, b.inc, b.ke, b.dscale, b.empty);
     k_sell_fill<4><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.row_of_vertex, b.adj_ptr, b.adj, b.inc_ptr, b.inc,
-                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col);
+                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col, b.dcoup);
   }
   return cudaGetLastError();
 }

@@ -5,23 +5,28 @@
 // The matrix is stored Jacobi-scaled (Khat = S K S), so preconditioned CG on K is plain CG
 // on Khat:  two kernels per iteration, no host involvement:
 //
-//   spmv  : p  = r + beta * p_old        (beta = rz_cur / rz_prev, from device scalars)
-//           q  = Khat p                  (block-SELL-32, one thread per 2x2 block row;
-//                                         p is formed on the fly at the gathered columns, so
-//                                         no separate p-update pass over HBM is needed)
-//           pq = p . q                   (warp shuffle -> CTA -> last-block-per-system)
-//   update: alpha = rz_cur / pq;  x += alpha p;  r -= alpha q;  rz_next = r . r
-//           convergence / breakdown / max-iter flags per system.
+//   spmv  : rz   = sum of the r.r partials the previous update left   -> convergence test
+//           p    = r + beta * p_old      (beta = rz / rz_prev)
+//           q    = Khat p                (block-SELL-32, one thread per 2x2 block row; p is formed
+//                                         on the fly at the gathered columns, so there is no
+//                                         separate p-update pass over HBM)
+//           partA[cta] = p . q over the CTA's rows
+//   update: pq   = sum of the p.q partials;  alpha = rz / pq
+//           x += alpha p;  r -= alpha q;  partB[cta] = r . r over the CTA's rows
 //
-// Every CTA (128 block rows) belongs to exactly one system.  Dot products are reduced in a
-// fixed order (thread -> warp tree -> CTA partial -> ordered sum by the last-arriving CTA of the
-// system), so results are bitwise reproducible and independent of how many systems share the
-// batch or the GPU.  Finished systems cost one flag read per CTA.
+// Every CTA (128 block rows) belongs to exactly one system.  Dot products never use atomics or
+// fences: a kernel leaves one partial per CTA and every warp of the *next* kernel re-adds the
+// partials of its own system in a fixed order (a few dozen L2-resident doubles).  Results are
+// therefore bitwise reproducible and independent of which other systems share the batch or the
+// GPU.  Systems owning more than kDirectSumMax CTAs (the ~1M-DOF single solves) get their partials
+// pre-summed by a one-CTA-per-system kernel between the two (two-level mode).  Finished systems
+// cost one flag read per CTA.
 #include "fea_internal.cuh"
 
 namespace fea {
 
-constexpr int kT = kCtaRows;  // threads per CTA
+constexpr int kT = kCtaRows;       // threads per CTA
+constexpr int kDirectSumMax = 128;  // partials a consumer warp sums itself
 
 // Deterministic CTA sum of one double per thread; result valid in thread 0.
 __device__ __forceinline__ double cta_sum(double v, double* sm /*[kT/32]*/) {
@@ -36,30 +41,11 @@ __device__ __forceinline__ double cta_sum(double v, double* sm /*[kT/32]*/) {
   return t;
 }
 
-// Publishes this CTA's partial; returns (to all threads) whether this CTA is the last of its
-// system to arrive, in which case *total (thread 0) holds the ordered sum of all partials.
-__device__ __forceinline__ bool system_reduce(double cta_partial, double* __restrict__ part,
-                                              unsigned int* __restrict__ cnt, int s, int first, int n,
-                                              double* sm, int* sm_flag, double* total) {
-  if (threadIdx.x == 0) {
-    part[blockIdx.x] = cta_partial;
-    __threadfence();
-    const unsigned prev = atomicAdd(&cnt[s], 1u);
-    *sm_flag = (prev == (unsigned)(n - 1));
-  }
-  __syncthreads();
-  const bool last = *sm_flag != 0;
-  if (!last) return false;
-  __threadfence();
+// Ordered sum of n partials, identical in every lane of every warp that calls it.
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int n) {
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += kT) acc += __ldcg(part + first + i);
-  __syncthreads();  // sm reuse
-  const double t = cta_sum(acc, sm);
-  if (threadIdx.x == 0) {
-    *total = t;
-    cnt[s] = 0u;
-  }
-  return true;
+  for (int i = threadIdx.x & 31; i < n; i += 32) acc += __ldg(part + i);
+  return warp_sum(acc);
 }
 
 struct PcgPtrs {
@@ -70,6 +56,7 @@ struct PcgPtrs {
   const int64_t* slice_ptr;
   const double2* val;
   const int32_t* col;
+  const double* dcoup;
   double2* x;
   double2* r;
   double2* q;
@@ -77,16 +64,38 @@ struct PcgPtrs {
   double* partB;
   SysScalars sc;
   double* rz_last;
+  int two_level;
 };
 
-__global__ void __launch_bounds__(kT) k_pcg_spmv(PcgPtrs P, const double2* __restrict__ p_old,
-                                                 double2* __restrict__ p_new, int parity, int check) {
+// U = entries whose loads are issued together before any of them is consumed (memory-level
+// parallelism per thread); MINB = minimum resident CTAs per SM asked of the register allocator.
+template <int U, int MINB>
+__global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(PcgPtrs P, const double2* __restrict__ p_old,
+                                                       double2* __restrict__ p_new, int parity, int max_iter) {
   __shared__ double sm[kT / 32];
-  __shared__ int sm_flag;
   const int s = P.sys_of_cta[blockIdx.x];
   if (s < 0) return;
   if (P.sc.done[s]) return;
-  const double beta = P.sc.rz[parity][s] / P.sc.rz[parity ^ 1][s];
+  const int first = P.cta_first[s];
+  const bool leader = (int)blockIdx.x == first && threadIdx.x == 0;
+  const double rz = P.two_level ? P.sc.psumB[s] : sum_partials(P.partB + first, P.cta_count[s]);
+  {
+    int st = -1;
+    if (!isfinite(rz)) st = FEA_SAMPLE_BREAKDOWN;
+    else if (rz <= P.sc.tol2[s]) st = FEA_SAMPLE_CONVERGED;
+    else if (P.sc.iters[s] >= max_iter) st = FEA_SAMPLE_MAX_ITER;
+    if (st >= 0) {  // every CTA of the system takes the same decision; the leader records it
+      if (leader) {
+        P.sc.done[s] = 1;
+        P.sc.status[s] = st;
+        P.rz_last[s] = rz;
+        atomicAdd(P.sc.n_done, 1);
+      }
+      return;
+    }
+  }
+  const double beta = rz / P.sc.rz[parity ^ 1][s];
+  if (leader) P.sc.rz[parity][s] = rz;
   const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int64_t slice = row >> 5;
@@ -95,48 +104,80 @@ __global__ void __launch_bounds__(kT) k_pcg_spmv(PcgPtrs P, const double2* __res
   const double2* __restrict__ vt = P.val + 2 * base + lane;
   const int32_t* __restrict__ cp = P.col + base + lane;
   const double2* __restrict__ r = P.r;
-  double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < L; ++j) {
-    const int c = ld_stream_i32(cp + j * 32);
-    const double2 t = ld_stream_f64x2(vt + j * 64);
-    const double2 b = ld_stream_f64x2(vt + j * 64 + 32);
-    const double2 rj = __ldg(r + c);
-    const double2 pj = __ldg(p_old + c);
-    const double px = fma(beta, pj.x, rj.x);
-    const double py = fma(beta, pj.y, rj.y);
-    a0 = fma(t.x, px, a0);
-    a0 = fma(t.y, py, a0);
-    a1 = fma(b.x, px, a1);
-    a1 = fma(b.y, py, a1);
-  }
+  // own row: p_i and the diagonal block [[1, a], [a, 1]]
   const double2 ri = __ldg(r + row);
   const double2 pi = __ldg(p_old + row);
+  const double dc = __ldg(P.dcoup + row);
   const double2 pn = make_double2(fma(beta, pi.x, ri.x), fma(beta, pi.y, ri.y));
+  double a0 = fma(dc, pn.y, pn.x), a1 = fma(dc, pn.x, pn.y);
+#pragma unroll 1
+  for (int j0 = 0; j0 < L; j0 += U) {
+    int c[U];
+    double2 t[U], b[U], rj[U], pj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = (j0 + u < L) ? ld_stream_i32(cp + (j0 + u) * 32) : (int)row;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      t[u] = make_double2(0.0, 0.0);
+      b[u] = make_double2(0.0, 0.0);
+      if (j0 + u < L) {
+        t[u] = ld_stream_f64x2(vt + (j0 + u) * 64);
+        b[u] = ld_stream_f64x2(vt + (j0 + u) * 64 + 32);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rj[u] = __ldg(r + c[u]);
+      pj[u] = __ldg(p_old + c[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double px = fma(beta, pj[u].x, rj[u].x);
+      const double py = fma(beta, pj[u].y, rj[u].y);
+      a0 = fma(t[u].x, px, a0);
+      a0 = fma(t[u].y, py, a0);
+      a1 = fma(b[u].x, px, a1);
+      a1 = fma(b[u].y, py, a1);
+    }
+  }
   p_new[row] = pn;
   P.q[row] = make_double2(a0, a1);
   const double part = cta_sum(fma(pn.x, a0, pn.y * a1), sm);
-  double total;
-  if (system_reduce(part, P.partA, P.sc.cntA, s, P.cta_first[s], P.cta_count[s], sm, &sm_flag, &total)) {
-    if (threadIdx.x == 0) {
-      P.sc.pq[s] = total;
-      if (check && !(total > 0.0 && isfinite(total))) {  // not SPD on this Krylov space
-        P.sc.done[s] = 1;
-        P.sc.status[s] = FEA_SAMPLE_BREAKDOWN;
-        atomicAdd(P.sc.n_done, 1);
-      }
-    }
+  if (threadIdx.x == 0) P.partA[blockIdx.x] = part;
+}
+
+typedef void (*spmv_fn)(PcgPtrs, const double2*, double2*, int, int);
+static spmv_fn pick_spmv(int variant) {
+  switch (variant) {
+    case 1: return k_pcg_spmv<1, 1>;
+    case 2: return k_pcg_spmv<2, 1>;
+    case 3: return k_pcg_spmv<3, 1>;
+    case 4: return k_pcg_spmv<4, 1>;
+    case 12: return k_pcg_spmv<2, 12>;
+    case 16: return k_pcg_spmv<2, 16>;
+    case 14: return k_pcg_spmv<4, 8>;
+    case 13: return k_pcg_spmv<3, 8>;
+    default: return k_pcg_spmv<2, 16>;
   }
 }
 
-__global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __restrict__ p, int parity,
-                                                   int max_iter) {
+__global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __restrict__ p, int parity) {
   __shared__ double sm[kT / 32];
-  __shared__ int sm_flag;
   const int s = P.sys_of_cta[blockIdx.x];
   if (s < 0) return;
   if (P.sc.done[s]) return;
-  const double alpha = P.sc.rz[parity][s] / P.sc.pq[s];
+  const int first = P.cta_first[s];
+  const bool leader = (int)blockIdx.x == first && threadIdx.x == 0;
+  const double pq = P.two_level ? P.sc.psumA[s] : sum_partials(P.partA + first, P.cta_count[s]);
+  if (!(pq > 0.0 && isfinite(pq))) {  // not SPD on this Krylov space (floating region, F4)
+    if (leader) {
+      P.sc.done[s] = 1;
+      P.sc.status[s] = FEA_SAMPLE_BREAKDOWN;
+      atomicAdd(P.sc.n_done, 1);
+    }
+    return;
+  }
+  const double alpha = P.sc.rz[parity][s] / pq;
   const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
   const double2 pv = p[row];
   const double2 qv = P.q[row];
@@ -149,33 +190,33 @@ __global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __r
   P.x[row] = xv;
   P.r[row] = rv;
   const double part = cta_sum(fma(rv.x, rv.x, rv.y * rv.y), sm);
-  double total;
-  if (system_reduce(part, P.partB, P.sc.cntB, s, P.cta_first[s], P.cta_count[s], sm, &sm_flag, &total)) {
-    if (threadIdx.x == 0) {
-      P.sc.rz[parity ^ 1][s] = total;
-      P.rz_last[s] = total;
-      const int it = P.sc.iters[s] + 1;
-      P.sc.iters[s] = it;
-      int st = -1;
-      if (!isfinite(total)) st = FEA_SAMPLE_BREAKDOWN;
-      else if (total <= P.sc.tol2[s]) st = FEA_SAMPLE_CONVERGED;
-      else if (it >= max_iter) st = FEA_SAMPLE_MAX_ITER;
-      if (st >= 0) {
-        P.sc.done[s] = 1;
-        P.sc.status[s] = st;
-        atomicAdd(P.sc.n_done, 1);
-      }
-    }
+  if (threadIdx.x == 0) {
+    P.partB[blockIdx.x] = part;
+    if (leader) P.sc.iters[s] += 1;
   }
 }
 
-// r0 = S b, x0 = 0, p = 0; r0.r0 per system; flags.
-__global__ void __launch_bounds__(kT) k_pcg_init(PcgPtrs P, const int32_t* __restrict__ vertex_of_row,
-                                                 const double* __restrict__ rhs, const double* __restrict__ dscale,
-                                                 double2* __restrict__ p0, double2* __restrict__ p1,
-                                                 const int32_t* __restrict__ empty, double rtol) {
+// two-level mode: one CTA per system pre-sums that system's partials in a fixed order
+__global__ void __launch_bounds__(kT) k_reduce_partials(const int32_t* __restrict__ cta_first,
+                                                        const int32_t* __restrict__ cta_count,
+                                                        const int32_t* __restrict__ done,
+                                                        const double* __restrict__ part, double* __restrict__ psum) {
   __shared__ double sm[kT / 32];
-  __shared__ int sm_flag;
+  const int s = blockIdx.x;
+  if (done[s]) return;
+  const int first = cta_first[s], n = cta_count[s];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kT) acc += __ldg(part + first + i);
+  const double t = cta_sum(acc, sm);
+  if (threadIdx.x == 0) psum[s] = t;
+}
+
+// r0 = S b, x0 = 0, p = 0; partB = r0.r0 partials.
+__global__ void __launch_bounds__(kT) k_pcg_init_vectors(PcgPtrs P, const int32_t* __restrict__ vertex_of_row,
+                                                         const double* __restrict__ rhs,
+                                                         const double* __restrict__ dscale,
+                                                         double2* __restrict__ p0, double2* __restrict__ p1) {
+  __shared__ double sm[kT / 32];
   const int s = P.sys_of_cta[blockIdx.x];
   if (s < 0) return;
   const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
@@ -189,25 +230,30 @@ __global__ void __launch_bounds__(kT) k_pcg_init(PcgPtrs P, const int32_t* __res
   p0[row] = z;
   p1[row] = z;
   const double part = cta_sum(fma(b.x, b.x, b.y * b.y), sm);
-  double total;
-  if (system_reduce(part, P.partB, P.sc.cntB, s, P.cta_first[s], P.cta_count[s], sm, &sm_flag, &total)) {
-    if (threadIdx.x == 0) {
-      P.sc.rz[0][s] = total;
-      P.sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);  // +inf -> beta_0 = 0
-      P.sc.rz0[s] = total;
-      P.rz_last[s] = total;
-      P.sc.tol2[s] = rtol * rtol * total;
-      P.sc.pq[s] = 1.0;
-      P.sc.iters[s] = 0;
-      P.sc.cntA[s] = 0u;
-      int st = FEA_SAMPLE_NOT_RUN, dn = 0;
-      if (empty[s]) { st = FEA_SAMPLE_EMPTY_ROW; dn = 1; }
-      else if (!(total > 0.0)) { st = isfinite(total) ? FEA_SAMPLE_CONVERGED : FEA_SAMPLE_BREAKDOWN; dn = 1; }
-      P.sc.status[s] = st;
-      P.sc.done[s] = dn;
-      if (dn) atomicAdd(P.sc.n_done, 1);
-    }
-  }
+  if (threadIdx.x == 0) P.partB[blockIdx.x] = part;
+}
+
+// one warp per system: r0.r0, tolerance, flags (also covers systems with no active vertex)
+__global__ void k_pcg_init_scalars(int ns, PcgPtrs P, const int32_t* __restrict__ empty, double rtol) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= ns) return;
+  const double total = sum_partials(P.partB + P.cta_first[s], P.cta_count[s]);
+  if ((threadIdx.x & 31) != 0) return;
+  P.sc.rz[0][s] = total;
+  P.sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);  // +inf -> beta_0 = 0
+  P.sc.rz0[s] = total;
+  P.rz_last[s] = total;
+  P.sc.tol2[s] = rtol * rtol * total;
+  P.sc.pq[s] = 1.0;
+  P.sc.psumA[s] = 1.0;
+  P.sc.psumB[s] = total;
+  P.sc.iters[s] = 0;
+  int st = FEA_SAMPLE_NOT_RUN, dn = 0;
+  if (empty[s]) { st = FEA_SAMPLE_EMPTY_ROW; dn = 1; }
+  else if (!(total > 0.0)) { st = isfinite(total) ? FEA_SAMPLE_CONVERGED : FEA_SAMPLE_BREAKDOWN; dn = 1; }
+  P.sc.status[s] = st;
+  P.sc.done[s] = dn;
+  if (dn) atomicAdd(P.sc.n_done, 1);
 }
 
 static PcgPtrs make_ptrs(Batch& b) {
@@ -219,6 +265,7 @@ static PcgPtrs make_ptrs(Batch& b) {
   P.slice_ptr = b.slice_ptr;
   P.val = b.val;
   P.col = b.col;
+  P.dcoup = b.dcoup;
   P.x = (double2*)b.x;
   P.r = (double2*)b.r;
   P.q = (double2*)b.q;
@@ -226,35 +273,43 @@ static PcgPtrs make_ptrs(Batch& b) {
   P.partB = b.partB;
   P.sc = b.sc;
   P.rz_last = b.rz_last;
+  P.two_level = b.max_cta_count > kDirectSumMax ? 1 : 0;
   return P;
 }
+
+// kernels launched per PCG iteration (bookkeeping)
+int pcg_launches_per_iteration(const Batch& b) { return b.max_cta_count > kDirectSumMax ? 4 : 2; }
 
 cudaError_t launch_pcg_init(Batch& b, double rtol) {
   const int ncta = (int)(b.NBR / kCtaRows);
   cudaStream_t st = b.ctx->stream;
   cudaMemsetAsync(b.sc.n_done, 0, sizeof(int32_t), st);
-  cudaMemsetAsync(b.sc.cntB, 0, sizeof(unsigned) * b.ns, st);
   if (ncta)
-    k_pcg_init<<<ncta, kT, 0, st>>>(make_ptrs(b), b.vertex_of_row, b.rhs, b.dscale, (double2*)b.p0,
-                                    (double2*)b.p1, b.empty, rtol);
+    k_pcg_init_vectors<<<ncta, kT, 0, st>>>(make_ptrs(b), b.vertex_of_row, b.rhs, b.dscale, (double2*)b.p0,
+                                            (double2*)b.p1);
+  k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(b.ns, make_ptrs(b), b.empty, rtol);
   return cudaGetLastError();
 }
 
 // iteration parity 0 reads p0 / writes p1, parity 1 the other way round
-cudaError_t launch_pcg_spmv(Batch& b, int parity, cudaStream_t st) {
+cudaError_t launch_pcg_spmv(Batch& b, int parity, int max_iter, cudaStream_t st) {
   const int ncta = (int)(b.NBR / kCtaRows);
   if (!ncta) return cudaSuccess;
+  const PcgPtrs P = make_ptrs(b);
   const double2* po = (const double2*)(parity ? b.p1 : b.p0);
   double2* pn = (double2*)(parity ? b.p0 : b.p1);
-  k_pcg_spmv<<<ncta, kT, 0, st>>>(make_ptrs(b), po, pn, parity, 1);
+  pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(P, po, pn, parity, max_iter);
+  if (P.two_level) k_reduce_partials<<<b.ns, kT, 0, st>>>(b.cta_first, b.cta_count, b.sc.done, b.partA, b.sc.psumA);
   return cudaGetLastError();
 }
 
-cudaError_t launch_pcg_update(Batch& b, int parity, int max_iter, cudaStream_t st) {
+cudaError_t launch_pcg_update(Batch& b, int parity, cudaStream_t st) {
   const int ncta = (int)(b.NBR / kCtaRows);
   if (!ncta) return cudaSuccess;
+  const PcgPtrs P = make_ptrs(b);
   const double2* pn = (const double2*)(parity ? b.p0 : b.p1);
-  k_pcg_update<<<ncta, kT, 0, st>>>(make_ptrs(b), pn, parity, max_iter);
+  k_pcg_update<<<ncta, kT, 0, st>>>(P, pn, parity);
+  if (P.two_level) k_reduce_partials<<<b.ns, kT, 0, st>>>(b.cta_first, b.cta_count, b.sc.done, b.partB, b.sc.psumB);
   return cudaGetLastError();
 }
 
@@ -366,13 +421,17 @@ __global__ void k_spmv_store(int64_t NBR, const int32_t* __restrict__ vertex_of_
     yout[2 * rk + 1] = s1 > 0 ? qv.y / s1 : 0.0;
   }
 }
-__global__ void k_spmv_scalars(int ns, SysScalars sc) {
+__global__ void k_spmv_scalars(int ns, SysScalars sc, const int32_t* __restrict__ cta_first,
+                               const int32_t* __restrict__ cta_count, double* __restrict__ partB) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns) return;
   sc.rz[0][s] = 1.0;
-  sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);
+  sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);  // beta = 0: p = r
   sc.done[s] = 0;
-  sc.cntA[s] = 0u;
+  sc.iters[s] = 0;
+  sc.tol2[s] = 0.0;
+  sc.psumB[s] = 1.0;
+  for (int i = 0; i < cta_count[s]; ++i) partB[cta_first[s] + i] = 1.0;  // "not converged"
 }
 
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y) {
@@ -382,9 +441,9 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
   if (!ncta) return cudaSuccess;
   const unsigned g = (unsigned)((b.NBR + T - 1) / T);
   const int64_t v0 = b.vtx_off[s], v1 = b.vtx_off[s + 1];
-  k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc);
+  k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc, b.cta_first, b.cta_count, b.partB);
   k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (double2*)b.r, (double2*)b.p0);
-  k_pcg_spmv<<<ncta, kT, 0, st>>>(make_ptrs(b), (const double2*)b.p0, (double2*)b.p1, 0, 0);
+  pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(make_ptrs(b), (const double2*)b.p0, (double2*)b.p1, 0, 1 << 30);
   k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, (const double2*)b.q, d_y);
   return cudaGetLastError();
 }

@@ -32,7 +32,8 @@ class Sample:
 class PackedBatch:
     """Concatenated, C-contiguous host arrays + the ctypes descriptor that points at them."""
 
-    def __init__(self, samples: Sequence[Sample]):
+    def __init__(self, samples: Sequence[Sample], alloc=None):
+        """``alloc(shape, dtype)`` may supply page-locked arrays (Context.pinned_empty)."""
         if not samples:
             raise ValueError("empty batch")
         k = samples[0].conn.shape[1]
@@ -46,7 +47,13 @@ class PackedBatch:
         self.vtx_off = np.concatenate([[0], np.cumsum(nv)]).astype(np.int64)
         self.cell_off = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
         self.reg_off = np.concatenate([[0], np.cumsum(nr)]).astype(np.int32)
-        cat = np.concatenate
+        def cat(parts):
+            a = np.concatenate(parts)
+            if alloc is None:
+                return a
+            out = alloc(a.shape, a.dtype)
+            out[...] = a
+            return out
         self.xy = np.ascontiguousarray(cat([np.asarray(s.coors, dtype=np.float64).reshape(-1, 2) for s in samples]))
         self.conn = np.ascontiguousarray(cat([np.asarray(s.conn, dtype=np.int32) for s in samples]))
         self.cell_region = np.ascontiguousarray(cat([np.asarray(s.cell_region, dtype=np.int8) for s in samples]))
@@ -72,8 +79,8 @@ class PackedBatch:
         return [a[self.vtx_off[s]:self.vtx_off[s + 1]] for s in range(self.n)]
 
 
-def pack(samples: Sequence[Sample]) -> PackedBatch:
-    return PackedBatch(samples)
+def pack(samples: Sequence[Sample], alloc=None) -> PackedBatch:
+    return PackedBatch(samples, alloc)
 
 
 @dataclass
@@ -120,6 +127,19 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.fea_ctx_synchronize(self.h))
+
+    def event_record(self, slot: int):
+        self._check(self.lib.fea_ctx_event_record(self.h, int(slot)))
+
+    def event_elapsed_ms(self, start: int, stop: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.fea_ctx_event_elapsed_ms(self.h, int(start), int(stop), C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.fea_ctx_kernel_launches(self.h, C.byref(n)))
+        return int(n.value)
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         """numpy array over page-locked host memory (fea_host_alloc); released by close()."""
@@ -217,6 +237,13 @@ class Batch:
         s = SolveStats()
         self.ctx._check(self.ctx.lib.fea_batch_get_solve_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def timed_launches(self):
+        """(spmv_ms, update_ms) arrays: launch t opened iteration 32*t of the last solve."""
+        a, u = np.zeros(64, np.float32), np.zeros(64, np.float32)
+        n = C.c_int32()
+        self.ctx._check(self.ctx.lib.fea_batch_get_timed_launches(self.h, 64, ptr(a), ptr(u), C.byref(n)))
+        return a[:n.value].copy(), u[:n.value].copy()
 
     def sample_sizes(self):
         n = self.packed.n

@@ -111,6 +111,12 @@ const char* fea_last_error(const fea_ctx* ctx);
 int  fea_host_alloc(fea_ctx* ctx, size_t bytes, void** out);
 int  fea_host_free(fea_ctx* ctx, void* p);
 int  fea_ctx_synchronize(fea_ctx* ctx);
+/* CUDA events on the context's stream, for timing regions that span several calls
+ * (slot in [0, 8)); elapsed is valid once the later event has completed. */
+int  fea_ctx_event_record(fea_ctx* ctx, int32_t slot);
+int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_stop, float* ms);
+/* number of kernels this context has launched so far (graph nodes included) */
+int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
 
 /* ---- batch life cycle ---------------------------------------------------
  * create   : H2D of the description; cell orientation fix (A-2); Dirichlet
@@ -143,6 +149,10 @@ int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
 int  fea_batch_download_images(fea_batch* b, uint8_t* images);
 int  fea_batch_get_info(fea_batch* b, fea_batch_info* out);
 int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
+/* CUDA-event durations of the SpMV / update launch that opens each chunk of 32 PCG iterations
+ * (launch t is iteration 32*t): at most cap entries are written, *n_out = number available. */
+int  fea_batch_get_timed_launches(fea_batch* b, int32_t cap, float* spmv_ms, float* update_ms,
+                                  int32_t* n_out);
 
 /* ---- inspection entry points used by the parity tests -------------------- */
 /* per-sample reduced sizes: n_active_dofs[s], nnz[s] (scalar CSR) */
