@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 
 # every symbol include/fea_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "fea_version", "fea_ctx_create", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
+    "fea_version", "fea_ctx_create", "fea_ctx_create_prio", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
     "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
@@ -85,6 +85,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     sig = {
         "fea_version": (C.c_int, [P, P]),
         "fea_ctx_create": (C.c_int, [C.c_int, C.POINTER(P)]),
+        "fea_ctx_create_prio": (C.c_int, [C.c_int, C.c_int, C.POINTER(P)]),
         "fea_ctx_destroy": (C.c_int, [P]),
         "fea_last_error": (C.c_char_p, [P]),
         "fea_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),

@@ -13,10 +13,6 @@ using namespace fea;
 
 struct fea_ctx {
   Ctx c;
-  int32_t* h_flag = nullptr;  // pinned [4]
-  std::vector<cudaEvent_t> events;
-  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
-  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_user[8] = {};
 };
 struct fea_batch {
@@ -25,9 +21,6 @@ struct fea_batch {
 };
 
 namespace {
-
-constexpr int kChunk = 32;      // PCG iterations between host polls (even)
-constexpr int kMaxTimed = 64;   // event-timed iterations per solve
 
 int fail(fea_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
   if (ctx) {
@@ -92,7 +85,9 @@ int fea_version(int* major, int* minor) {
   return FEA_OK;
 }
 
-int fea_ctx_create(int device, fea_ctx** out) {
+int fea_ctx_create(int device, fea_ctx** out) { return fea_ctx_create_prio(device, 0, out); }
+
+int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   if (!out) return FEA_BAD_ARG;
   *out = nullptr;
   fea_ctx* ctx = new (std::nothrow) fea_ctx();
@@ -100,7 +95,10 @@ int fea_ctx_create(int device, fea_ctx** out) {
   ctx->c.device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
-  if ((e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent (numerically largest)
+  priority = std::max(hi, std::min(lo, priority));
+  if ((e = cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, priority)) != cudaSuccess) { delete ctx; return FEA_CUDA_ERROR; }
   cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("FEA_SPMV_VARIANT")) ctx->c.spmv_variant = atoi(v);
   cudaMemPool_t pool;
@@ -108,18 +106,22 @@ int fea_ctx_create(int device, fea_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  if (cudaHostAlloc((void**)&ctx->h_flag, 4 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+  if (const char* v = getenv("FEA_NO_GRAPHS")) ctx->c.use_graphs = atoi(v) ? 0 : 1;
+  if (cudaHostAlloc((void**)&ctx->c.h_flag, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+      cudaMalloc(&ctx->c.d_pcg_params, kPcgParamBytes) != cudaSuccess) {
+    if (ctx->c.h_flag) cudaFreeHost(ctx->c.h_flag);
     cudaStreamDestroy(ctx->c.stream);
     delete ctx;
+    cudaGetLastError();
     return FEA_CUDA_ERROR;
   }
-  cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming);
-  cudaEventCreate(&ctx->ev_t0);
-  cudaEventCreate(&ctx->ev_t1);
+  cudaEventCreateWithFlags(&ctx->c.ev_poll[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->c.ev_poll[1], cudaEventDisableTiming);
+  cudaEventCreate(&ctx->c.ev_t0);
+  cudaEventCreate(&ctx->c.ev_t1);
   for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
-  ctx->events.resize(3 * kMaxTimed);
-  for (auto& ev : ctx->events) cudaEventCreate(&ev);
+  ctx->c.events.resize(3 * kMaxTimed);
+  for (auto& ev : ctx->c.events) cudaEventCreate(&ev);
   *out = ctx;
   return FEA_OK;
 }
@@ -128,13 +130,15 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   if (!ctx) return FEA_OK;
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
-  for (auto& ev : ctx->events) cudaEventDestroy(ev);
-  cudaEventDestroy(ctx->ev_poll[0]);
-  cudaEventDestroy(ctx->ev_poll[1]);
-  cudaEventDestroy(ctx->ev_t0);
-  cudaEventDestroy(ctx->ev_t1);
+  pcg_release(ctx->c);
+  for (auto& ev : ctx->c.events) cudaEventDestroy(ev);
+  cudaEventDestroy(ctx->c.ev_poll[0]);
+  cudaEventDestroy(ctx->c.ev_poll[1]);
+  cudaEventDestroy(ctx->c.ev_t0);
+  cudaEventDestroy(ctx->c.ev_t1);
   for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
-  cudaFreeHost(ctx->h_flag);
+  cudaFreeHost(ctx->c.h_flag);
+  cudaFree(ctx->c.d_pcg_params);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
   return FEA_OK;
@@ -198,7 +202,6 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   hb->owner = ctx;
   Batch& b = hb->b;
   b.ctx = &ctx->c;
-  b.h_flag = ctx->h_flag;
   b.ns = ns;
   b.npc = d->nodes_per_cell;
   b.vtx_off.assign(d->vtx_off, d->vtx_off + ns + 1);
@@ -317,6 +320,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.p1, b.NBR * 2));
   CK(ctx, dalloc(b, &b.q, b.NBR * 2));
   const int64_t ncta = b.NBR / kCtaRows;
+  CK(ctx, dalloc(b, &b.active_cta, 4 * ncta));  // int4 entries
   CK(ctx, dalloc(b, &b.partA, ncta));
   CK(ctx, dalloc(b, &b.partB, ncta));
   CK(ctx, dalloc(b, &b.sc.rz[0], b.ns));
@@ -350,99 +354,7 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
   if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_solve before fea_batch_assemble");
   if (!(rtol >= 0.0) || max_iter < 1) return fail(ctx, FEA_BAD_ARG, "rtol must be >= 0 and max_iter >= 1");
   CK(ctx, cudaSetDevice(ctx->c.device));
-  cudaStream_t st = ctx->c.stream;
-  b.stats = fea_solve_stats{};
-  int64_t launches = 0;
-  CK(ctx, cudaEventRecord(ctx->ev_t0, st));
-  CK(ctx, launch_pcg_init(b, rtol));
-  launches += 2;
-  // capture kChunk-2 iterations once; the first two iterations of every chunk are plain
-  // launches so that one spmv/update pair per chunk can be bracketed by timing events
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
-  CK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  for (int i = 2; i < kChunk; ++i) {
-    launch_pcg_spmv(b, i & 1, max_iter, st);
-    launch_pcg_update(b, i & 1, st);
-  }
-  CK(ctx, cudaStreamEndCapture(st, &graph));
-  CK(ctx, cudaGraphInstantiate(&exec, graph, 0));
-  const int max_chunks = (max_iter + kChunk - 1) / kChunk + 2;
-  std::vector<int> done_after;  // n_done observed after chunk k
-  int timed = 0;
-  int k = 0;
-  cudaError_t e = cudaSuccess;
-  for (; k < max_chunks; ++k) {
-    if (timed < kMaxTimed) {
-      cudaEventRecord(ctx->events[3 * timed], st);
-      launch_pcg_spmv(b, 0, max_iter, st);
-      cudaEventRecord(ctx->events[3 * timed + 1], st);
-      launch_pcg_update(b, 0, st);
-      cudaEventRecord(ctx->events[3 * timed + 2], st);
-      ++timed;
-    } else {
-      launch_pcg_spmv(b, 0, max_iter, st);
-      launch_pcg_update(b, 0, st);
-    }
-    launch_pcg_spmv(b, 1, max_iter, st);
-    launch_pcg_update(b, 1, st);
-    e = cudaGraphLaunch(exec, st);
-    if (e != cudaSuccess) break;
-    launches += (int64_t)pcg_launches_per_iteration(b) * kChunk;
-    cudaMemcpyAsync(&b.h_flag[k & 1], b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    cudaEventRecord(ctx->ev_poll[k & 1], st);
-    if (k >= 1) {
-      e = cudaEventSynchronize(ctx->ev_poll[(k - 1) & 1]);
-      if (e != cudaSuccess) break;
-      done_after.push_back(b.h_flag[(k - 1) & 1]);
-      if (b.h_flag[(k - 1) & 1] >= b.ns) { ++k; break; }
-    }
-  }
-  if (e == cudaSuccess) e = launch_finalize(b);
-  launches += 3;
-  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_t1, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaGraphExecDestroy(exec);
-  cudaGraphDestroy(graph);
-  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_solve", e);
-  // statistics
-  std::vector<int32_t> it(b.ns), stt(b.ns);
-  CK(ctx, cudaMemcpy(it.data(), b.sc.iters, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
-  CK(ctx, cudaMemcpy(stt.data(), b.sc.status, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost));
-  b.stats.iterations = *std::max_element(it.begin(), it.end());
-  b.stats.n_converged = (int32_t)std::count(stt.begin(), stt.end(), (int32_t)FEA_SAMPLE_CONVERGED);
-  // average only over timed launches that ran with every system still active
-  double sa = 0, su = 0;
-  int na = 0;
-  b.t_spmv.assign(timed, 0.f);
-  b.t_update.assign(timed, 0.f);
-  for (int t = 0; t < timed; ++t) {
-    cudaEventElapsedTime(&b.t_spmv[t], ctx->events[3 * t], ctx->events[3 * t + 1]);
-    cudaEventElapsedTime(&b.t_update[t], ctx->events[3 * t + 1], ctx->events[3 * t + 2]);
-  }
-  for (int t = 0; t < timed; ++t) {
-    // (a few systems may finish at once, e.g. loads that fall on constrained vertices)
-    const bool all_active = (t == 0) || (t - 1 < (int)done_after.size() && done_after[t - 1] * 20 <= b.ns);
-    if (!all_active) break;
-    float a = 0, u = 0;
-    cudaEventElapsedTime(&a, ctx->events[3 * t], ctx->events[3 * t + 1]);
-    cudaEventElapsedTime(&u, ctx->events[3 * t + 1], ctx->events[3 * t + 2]);
-    sa += a;
-    su += u;
-    ++na;
-  }
-  if (getenv("FEA_DEBUG")) {
-    fprintf(stderr, "[fea] solve: chunks=%d timed=%d na=%d done_after:", k, timed, na);
-    for (size_t i = 0; i < done_after.size() && i < 24; ++i) fprintf(stderr, " %d", done_after[i]);
-    fprintf(stderr, "\n");
-  }
-  b.stats.spmv_launches_timed = na;
-  b.stats.update_launches_timed = na;
-  b.stats.spmv_ms_avg = na ? (float)(sa / na) : 0.f;
-  b.stats.update_ms_avg = na ? (float)(su / na) : 0.f;
-  cudaEventElapsedTime(&b.stats.solve_ms, ctx->ev_t0, ctx->ev_t1);
-  b.stats.kernel_launches = launches;
-  ctx->c.launches += launches;
+  CK(ctx, run_pcg(b, rtol, max_iter));
   b.solved = true;
   return FEA_OK;
 }

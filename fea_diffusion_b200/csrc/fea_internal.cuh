@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -16,11 +17,23 @@ constexpr int kCtaRows = 128;   // block rows per CTA in the solver kernels
 constexpr int kMaxAdj = 64;     // supported vertex valence + 1
 constexpr int kMaxSamplesPerBatch = 1 << 20;
 
+constexpr int kChunk = 32;      // PCG iterations between host polls (even)
+constexpr int kMaxTimed = 64;   // event-timed iterations per solve
+constexpr int kPcgParamBytes = 512;  // device buffer for the solver's parameter block
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   int sm_count = 148;
+  // PCG driver state, owned by the context so that CUDA graphs survive across solves
+  int32_t* h_flag = nullptr;           // pinned [8]: polled counters
+  void* d_pcg_params = nullptr;        // device copy of the current solve's PcgPtrs
+  std::map<int64_t, cudaGraphExec_t> pcg_graphs;  // key: grid size class * 2 + two_level
+  std::vector<cudaEvent_t> events;     // 3 per timed launch
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  int use_graphs = 1;                  // env FEA_NO_GRAPHS=1 disables
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
   int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };
@@ -72,6 +85,7 @@ struct Batch {
   int32_t* cta_first = nullptr;      // [ns] first CTA of the system
   int32_t* cta_count = nullptr;      // [ns]
   int32_t max_cta_count = 0;         // host copy: most CTAs any one system owns
+  int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending
@@ -107,8 +121,6 @@ struct Batch {
   double* affine = nullptr;  // [ns*4]
   fea_solve_stats stats{};
   std::vector<float> t_spmv, t_update;  // per timed launch (one per chunk)
-  // pinned host scratch
-  int32_t* h_flag = nullptr;
 };
 
 // ---- launchers implemented in the kernel translation units -----------------
@@ -121,10 +133,9 @@ cudaError_t launch_sell_lengths(Batch& b);                    // slice_len + sli
 cudaError_t launch_sell_fill(Batch& b);                       // dscale, val, col
 cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d_indices,
                               double* d_data);
-cudaError_t launch_pcg_init(Batch& b, double rtol);
-cudaError_t launch_pcg_spmv(Batch& b, int parity, int max_iter, cudaStream_t st);
-cudaError_t launch_pcg_update(Batch& b, int parity, cudaStream_t st);
-int pcg_launches_per_iteration(const Batch& b);
+// whole lock-step PCG loop (init, chunks of kChunk iterations, polling); fills b.stats / timings
+cudaError_t run_pcg(Batch& b, double rtol, int max_iter);
+void pcg_release(Ctx& c);                                     // destroys the cached graphs
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);

@@ -21,6 +21,9 @@
 // GPU.  Systems owning more than kDirectSumMax CTAs (the ~1M-DOF single solves) get their partials
 // pre-summed by a one-CTA-per-system kernel between the two (two-level mode).  Finished systems
 // cost one flag read per CTA.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fea_internal.cuh"
 
 namespace fea {
@@ -48,6 +51,9 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
   return warp_sum(acc);
 }
 
+// Everything the solver kernels need, resident in device memory (Ctx::d_pcg_params) instead of
+// being passed by value: the kernel nodes of an instantiated CUDA graph then carry no batch
+// pointers, so one graph per grid size serves every batch the context ever solves.
 struct PcgPtrs {
   const int32_t* sys_of_cta;
   const int32_t* cta_first;
@@ -60,30 +66,38 @@ struct PcgPtrs {
   double2* x;
   double2* r;
   double2* q;
+  double2* p[2];     // iteration parity 0 reads p[0] / writes p[1], parity 1 the other way round
   double* partA;
   double* partB;
   SysScalars sc;
   double* rz_last;
-  int two_level;
+  int4* active;      // compacted work list: (cta, system, first cta of system, cta count)
+  int32_t n_active;  // valid entries of `active` (written by k_compact_active)
+  int32_t ncta;      // CTAs of the whole batch
+  int32_t ns;
+  int32_t max_iter;
+  int32_t two_level;
 };
+static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
 
 // U = entries whose loads are issued together before any of them is consumed (memory-level
 // parallelism per thread); MINB = minimum resident CTAs per SM asked of the register allocator.
+// Grid = any size >= P.n_active (the host picks a size class from a slightly stale count).
 template <int U, int MINB>
-__global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(PcgPtrs P, const double2* __restrict__ p_old,
-                                                       double2* __restrict__ p_new, int parity, int max_iter) {
+__global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict__ Pp, int parity) {
   __shared__ double sm[kT / 32];
-  const int s = P.sys_of_cta[blockIdx.x];
-  if (s < 0) return;
+  const PcgPtrs& P = *Pp;
+  if ((int)blockIdx.x >= P.n_active) return;
+  const int4 w = __ldg(P.active + blockIdx.x);
+  const int cta = w.x, s = w.y, first = w.z;
   if (P.sc.done[s]) return;
-  const int first = P.cta_first[s];
-  const bool leader = (int)blockIdx.x == first && threadIdx.x == 0;
-  const double rz = P.two_level ? P.sc.psumB[s] : sum_partials(P.partB + first, P.cta_count[s]);
+  const bool leader = cta == first && threadIdx.x == 0;
+  const double rz = P.two_level ? P.sc.psumB[s] : sum_partials(P.partB + first, w.w);
   {
     int st = -1;
     if (!isfinite(rz)) st = FEA_SAMPLE_BREAKDOWN;
     else if (rz <= P.sc.tol2[s]) st = FEA_SAMPLE_CONVERGED;
-    else if (P.sc.iters[s] >= max_iter) st = FEA_SAMPLE_MAX_ITER;
+    else if (P.sc.iters[s] >= P.max_iter) st = FEA_SAMPLE_MAX_ITER;
     if (st >= 0) {  // every CTA of the system takes the same decision; the leader records it
       if (leader) {
         P.sc.done[s] = 1;
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(PcgPtrs P, const double2*
   }
   const double beta = rz / P.sc.rz[parity ^ 1][s];
   if (leader) P.sc.rz[parity][s] = rz;
-  const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
+  const int64_t row = (int64_t)cta * kT + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int64_t slice = row >> 5;
   const int L = P.slice_len[slice];
@@ -104,6 +118,7 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(PcgPtrs P, const double2*
   const double2* __restrict__ vt = P.val + 2 * base + lane;
   const int32_t* __restrict__ cp = P.col + base + lane;
   const double2* __restrict__ r = P.r;
+  const double2* __restrict__ p_old = P.p[parity];
   // own row: p_i and the diagonal block [[1, a], [a, 1]]
   const double2 ri = __ldg(r + row);
   const double2 pi = __ldg(p_old + row);
@@ -140,13 +155,13 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(PcgPtrs P, const double2*
       a1 = fma(b[u].y, py, a1);
     }
   }
-  p_new[row] = pn;
+  P.p[parity ^ 1][row] = pn;
   P.q[row] = make_double2(a0, a1);
   const double part = cta_sum(fma(pn.x, a0, pn.y * a1), sm);
-  if (threadIdx.x == 0) P.partA[blockIdx.x] = part;
+  if (threadIdx.x == 0) P.partA[cta] = part;
 }
 
-typedef void (*spmv_fn)(PcgPtrs, const double2*, double2*, int, int);
+typedef void (*spmv_fn)(const PcgPtrs*, int);
 static spmv_fn pick_spmv(int variant) {
   switch (variant) {
     case 1: return k_pcg_spmv<1, 1>;
@@ -161,14 +176,15 @@ static spmv_fn pick_spmv(int variant) {
   }
 }
 
-__global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __restrict__ p, int parity) {
+__global__ void __launch_bounds__(kT) k_pcg_update(const PcgPtrs* __restrict__ Pp, int parity) {
   __shared__ double sm[kT / 32];
-  const int s = P.sys_of_cta[blockIdx.x];
-  if (s < 0) return;
+  const PcgPtrs& P = *Pp;
+  if ((int)blockIdx.x >= P.n_active) return;
+  const int4 w = __ldg(P.active + blockIdx.x);
+  const int cta = w.x, s = w.y, first = w.z;
   if (P.sc.done[s]) return;
-  const int first = P.cta_first[s];
-  const bool leader = (int)blockIdx.x == first && threadIdx.x == 0;
-  const double pq = P.two_level ? P.sc.psumA[s] : sum_partials(P.partA + first, P.cta_count[s]);
+  const bool leader = cta == first && threadIdx.x == 0;
+  const double pq = P.two_level ? P.sc.psumA[s] : sum_partials(P.partA + first, w.w);
   if (!(pq > 0.0 && isfinite(pq))) {  // not SPD on this Krylov space (floating region, F4)
     if (leader) {
       P.sc.done[s] = 1;
@@ -178,8 +194,8 @@ __global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __r
     return;
   }
   const double alpha = P.sc.rz[parity][s] / pq;
-  const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
-  const double2 pv = p[row];
+  const int64_t row = (int64_t)cta * kT + threadIdx.x;
+  const double2 pv = P.p[parity ^ 1][row];
   const double2 qv = P.q[row];
   double2 xv = P.x[row];
   double2 rv = P.r[row];
@@ -191,32 +207,73 @@ __global__ void __launch_bounds__(kT) k_pcg_update(PcgPtrs P, const double2* __r
   P.r[row] = rv;
   const double part = cta_sum(fma(rv.x, rv.x, rv.y * rv.y), sm);
   if (threadIdx.x == 0) {
-    P.partB[blockIdx.x] = part;
+    P.partB[cta] = part;
     if (leader) P.sc.iters[s] += 1;
   }
 }
 
 // two-level mode: one CTA per system pre-sums that system's partials in a fixed order
-__global__ void __launch_bounds__(kT) k_reduce_partials(const int32_t* __restrict__ cta_first,
-                                                        const int32_t* __restrict__ cta_count,
-                                                        const int32_t* __restrict__ done,
-                                                        const double* __restrict__ part, double* __restrict__ psum) {
+__global__ void __launch_bounds__(kT) k_reduce_partials(const PcgPtrs* __restrict__ Pp, int which) {
   __shared__ double sm[kT / 32];
-  const int s = blockIdx.x;
-  if (done[s]) return;
-  const int first = cta_first[s], n = cta_count[s];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += kT) acc += __ldg(part + first + i);
-  const double t = cta_sum(acc, sm);
-  if (threadIdx.x == 0) psum[s] = t;
+  const PcgPtrs& P = *Pp;
+  const double* __restrict__ part = which ? P.partB : P.partA;
+  double* psum = which ? P.sc.psumB : P.sc.psumA;
+  for (int s = blockIdx.x; s < P.ns; s += gridDim.x) {
+    if (P.sc.done[s]) continue;
+    const int first = P.cta_first[s], n = P.cta_count[s];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += kT) acc += __ldg(part + first + i);
+    const double t = cta_sum(acc, sm);
+    if (threadIdx.x == 0) psum[s] = t;
+    __syncthreads();
+  }
+}
+
+// Work list of the CTAs whose system is still iterating, in CTA order (one CTA does the whole
+// compaction: a batch has at most a few 10^4 solver CTAs).  Runs once per chunk of iterations;
+// systems that finish inside a chunk cost one flag read per CTA until the next compaction.
+__global__ void __launch_bounds__(1024) k_compact_active(PcgPtrs* __restrict__ Pp) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const PcgPtrs& P = *Pp;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < P.ncta; base += 1024) {
+    const int c = base + threadIdx.x;
+    int s = -1;
+    if (c < P.ncta) {
+      s = P.sys_of_cta[c];
+      if (s >= 0 && P.sc.done[s]) s = -1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, s >= 0);
+    if (lane == 0) wsum[wid] = __popc(m);
+    __syncthreads();
+    int off = carry;
+    for (int i = 0; i < wid; ++i) off += wsum[i];
+    if (s >= 0) P.active[off + __popc(m & ((1u << lane) - 1u))] = make_int4(c, s, P.cta_first[s], P.cta_count[s]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int i = 0; i < 32; ++i) t += wsum[i];
+      carry += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) Pp->n_active = carry;
+}
+
+__global__ void k_store_params(PcgPtrs P, PcgPtrs* __restrict__ dst) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = P;
 }
 
 // r0 = S b, x0 = 0, p = 0; partB = r0.r0 partials.
-__global__ void __launch_bounds__(kT) k_pcg_init_vectors(PcgPtrs P, const int32_t* __restrict__ vertex_of_row,
+__global__ void __launch_bounds__(kT) k_pcg_init_vectors(const PcgPtrs* __restrict__ Pp,
+                                                         const int32_t* __restrict__ vertex_of_row,
                                                          const double* __restrict__ rhs,
-                                                         const double* __restrict__ dscale,
-                                                         double2* __restrict__ p0, double2* __restrict__ p1) {
+                                                         const double* __restrict__ dscale) {
   __shared__ double sm[kT / 32];
+  const PcgPtrs& P = *Pp;
   const int s = P.sys_of_cta[blockIdx.x];
   if (s < 0) return;
   const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
@@ -227,16 +284,17 @@ __global__ void __launch_bounds__(kT) k_pcg_init_vectors(PcgPtrs P, const int32_
   P.x[row] = z;
   P.r[row] = b;
   P.q[row] = z;
-  p0[row] = z;
-  p1[row] = z;
+  P.p[0][row] = z;
+  P.p[1][row] = z;
   const double part = cta_sum(fma(b.x, b.x, b.y * b.y), sm);
   if (threadIdx.x == 0) P.partB[blockIdx.x] = part;
 }
 
 // one warp per system: r0.r0, tolerance, flags (also covers systems with no active vertex)
-__global__ void k_pcg_init_scalars(int ns, PcgPtrs P, const int32_t* __restrict__ empty, double rtol) {
+__global__ void k_pcg_init_scalars(const PcgPtrs* __restrict__ Pp, const int32_t* __restrict__ empty, double rtol) {
+  const PcgPtrs& P = *Pp;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= ns) return;
+  if (s >= P.ns) return;
   const double total = sum_partials(P.partB + P.cta_first[s], P.cta_count[s]);
   if ((threadIdx.x & 31) != 0) return;
   P.sc.rz[0][s] = total;
@@ -256,7 +314,7 @@ __global__ void k_pcg_init_scalars(int ns, PcgPtrs P, const int32_t* __restrict_
   if (dn) atomicAdd(P.sc.n_done, 1);
 }
 
-static PcgPtrs make_ptrs(Batch& b) {
+static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   PcgPtrs P;
   P.sys_of_cta = b.sys_of_cta;
   P.cta_first = b.cta_first;
@@ -269,48 +327,176 @@ static PcgPtrs make_ptrs(Batch& b) {
   P.x = (double2*)b.x;
   P.r = (double2*)b.r;
   P.q = (double2*)b.q;
+  P.p[0] = (double2*)b.p0;
+  P.p[1] = (double2*)b.p1;
   P.partA = b.partA;
   P.partB = b.partB;
   P.sc = b.sc;
   P.rz_last = b.rz_last;
+  P.active = (int4*)b.active_cta;
+  P.n_active = 0;
+  P.ncta = (int32_t)(b.NBR / kCtaRows);
+  P.ns = b.ns;
+  P.max_iter = max_iter;
   P.two_level = b.max_cta_count > kDirectSumMax ? 1 : 0;
   return P;
 }
 
-// kernels launched per PCG iteration (bookkeeping)
-int pcg_launches_per_iteration(const Batch& b) { return b.max_cta_count > kDirectSumMax ? 4 : 2; }
+// one iteration (2 kernels, 4 in two-level mode) on a grid of g CTAs
+static void launch_iteration(Ctx& c, const PcgPtrs* dP, int g, int parity, bool two_level, int ns, cudaStream_t st) {
+  const int gr = ns < 1024 ? ns : 1024;
+  pick_spmv(c.spmv_variant)<<<g, kT, 0, st>>>(dP, parity);
+  if (two_level) k_reduce_partials<<<gr, kT, 0, st>>>(dP, 0);
+  k_pcg_update<<<g, kT, 0, st>>>(dP, parity);
+  if (two_level) k_reduce_partials<<<gr, kT, 0, st>>>(dP, 1);
+}
 
-cudaError_t launch_pcg_init(Batch& b, double rtol) {
+// grid size classes: 148 * 2^(j/2), so a stale count costs at most ~41% idle CTAs
+static int grid_class(int n_active, int ncta) {
+  double g = 148.0;
+  while ((int)g < n_active) g *= 1.4142135623730951;
+  const int gi = (int)g;
+  return gi < ncta ? gi : ncta;
+}
+
+static cudaError_t get_chunk_graph(Ctx& c, const PcgPtrs* dP, int g, bool two_level, int ns, cudaGraphExec_t* out) {
+  const int64_t key = ((int64_t)g << 32) | ((int64_t)(two_level ? (ns < 1024 ? ns : 1024) : 0) << 1) | (two_level ? 1 : 0);
+  auto it = c.pcg_graphs.find(key);
+  if (it != c.pcg_graphs.end()) { *out = it->second; return cudaSuccess; }
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return e;
+  for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, two_level, ns, c.stream);
+  k_compact_active<<<1, 1024, 0, c.stream>>>((PcgPtrs*)dP);
+  e = cudaStreamEndCapture(c.stream, &graph);
+  if (e != cudaSuccess) return e;
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return e;
+  if (c.pcg_graphs.size() >= 256) {  // batches of many different sizes: start over
+    for (auto& kv : c.pcg_graphs) cudaGraphExecDestroy(kv.second);
+    c.pcg_graphs.clear();
+  }
+  c.pcg_graphs[key] = exec;
+  *out = exec;
+  return cudaSuccess;
+}
+
+// The whole lock-step solve.  Per chunk of kChunk iterations: two plain iterations (the first one
+// bracketed by timing events), a cached graph of kChunk-2 iterations + work-list compaction, and
+// an async read-back of (finished systems, active CTAs) that the host consumes one chunk late, so
+// the stream never drains while systems are still iterating.
+cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
+  Ctx& c = *b.ctx;
+  cudaStream_t st = c.stream;
   const int ncta = (int)(b.NBR / kCtaRows);
-  cudaStream_t st = b.ctx->stream;
+  PcgPtrs* dP = (PcgPtrs*)c.d_pcg_params;
+  const PcgPtrs P = make_ptrs(b, max_iter);
+  const bool two = P.two_level != 0;
+  const int per_iter = two ? 4 : 2;
+  int64_t launches = 0;
+  cudaError_t e;
+  b.stats = fea_solve_stats{};
+  b.t_spmv.clear();
+  b.t_update.clear();
+  if ((e = cudaEventRecord(c.ev_t0, st)) != cudaSuccess) return e;
+  k_store_params<<<1, 32, 0, st>>>(P, dP);
   cudaMemsetAsync(b.sc.n_done, 0, sizeof(int32_t), st);
-  if (ncta)
-    k_pcg_init_vectors<<<ncta, kT, 0, st>>>(make_ptrs(b), b.vertex_of_row, b.rhs, b.dscale, (double2*)b.p0,
-                                            (double2*)b.p1);
-  k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(b.ns, make_ptrs(b), b.empty, rtol);
-  return cudaGetLastError();
+  if (ncta) k_pcg_init_vectors<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
+  k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
+  k_compact_active<<<1, 1024, 0, st>>>(dP);
+  launches += 4;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  std::vector<int> done_after;  // finished systems observed after chunk k
+  int timed = 0, k = 0;
+  if (ncta) {
+    const int max_chunks = (max_iter + kChunk - 1) / kChunk + 2;
+    int n_active = ncta;  // stale upper bound of the work-list length
+    for (; k < max_chunks; ++k) {
+      const int g = grid_class(n_active, ncta);
+      cudaGraphExec_t exec = nullptr;
+      if (c.use_graphs && (e = get_chunk_graph(c, dP, g, two, b.ns, &exec)) != cudaSuccess) return e;
+      const bool t = timed < kMaxTimed;
+      if (t) cudaEventRecord(c.events[3 * timed], st);
+      pick_spmv(c.spmv_variant)<<<g, kT, 0, st>>>(dP, 0);
+      if (two) k_reduce_partials<<<b.ns < 1024 ? b.ns : 1024, kT, 0, st>>>(dP, 0);
+      if (t) cudaEventRecord(c.events[3 * timed + 1], st);
+      k_pcg_update<<<g, kT, 0, st>>>(dP, 0);
+      if (two) k_reduce_partials<<<b.ns < 1024 ? b.ns : 1024, kT, 0, st>>>(dP, 1);
+      if (t) { cudaEventRecord(c.events[3 * timed + 2], st); ++timed; }
+      launch_iteration(c, dP, g, 1, two, b.ns, st);
+      if (exec) {
+        if ((e = cudaGraphLaunch(exec, st)) != cudaSuccess) return e;
+      } else {
+        for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, two, b.ns, st);
+        k_compact_active<<<1, 1024, 0, st>>>(dP);
+      }
+      launches += (int64_t)per_iter * kChunk + 1;
+      int32_t* hf = c.h_flag + 2 * (k & 1);
+      cudaMemcpyAsync(hf, b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hf + 1, &dP->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(c.ev_poll[k & 1], st);
+      if (k >= 1) {
+        if ((e = cudaEventSynchronize(c.ev_poll[(k - 1) & 1])) != cudaSuccess) return e;
+        const int32_t* hp = c.h_flag + 2 * ((k - 1) & 1);
+        done_after.push_back(hp[0]);
+        n_active = hp[1];
+        if (hp[0] >= b.ns) { ++k; break; }
+      }
+    }
+  }
+  if ((e = launch_finalize(b)) != cudaSuccess) return e;
+  launches += 3;
+  if ((e = cudaEventRecord(c.ev_t1, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  // statistics
+  std::vector<int32_t> it(b.ns), stt(b.ns);
+  if ((e = cudaMemcpyAsync(it.data(), b.sc.iters, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(stt.data(), b.sc.status, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  int itmax = 0, nconv = 0;
+  for (int s = 0; s < b.ns; ++s) {
+    itmax = it[s] > itmax ? it[s] : itmax;
+    nconv += stt[s] == FEA_SAMPLE_CONVERGED;
+  }
+  b.stats.iterations = itmax;
+  b.stats.n_converged = nconv;
+  b.t_spmv.assign(timed, 0.f);
+  b.t_update.assign(timed, 0.f);
+  for (int t = 0; t < timed; ++t) {
+    cudaEventElapsedTime(&b.t_spmv[t], c.events[3 * t], c.events[3 * t + 1]);
+    cudaEventElapsedTime(&b.t_update[t], c.events[3 * t + 1], c.events[3 * t + 2]);
+  }
+  // average only over timed launches that ran with (nearly) every system still active
+  // (a few systems may finish at once, e.g. loads that fall on constrained vertices)
+  double sa = 0, su = 0;
+  int na = 0;
+  for (int t = 0; t < timed; ++t) {
+    const bool all_active = (t == 0) || (t - 1 < (int)done_after.size() && done_after[t - 1] * 20 <= b.ns);
+    if (!all_active) break;
+    sa += b.t_spmv[t];
+    su += b.t_update[t];
+    ++na;
+  }
+  if (getenv("FEA_DEBUG")) {
+    fprintf(stderr, "[fea] solve: chunks=%d timed=%d na=%d graphs=%zu done_after:", k, timed, na, c.pcg_graphs.size());
+    for (size_t i = 0; i < done_after.size() && i < 24; ++i) fprintf(stderr, " %d", done_after[i]);
+    fprintf(stderr, "\n");
+  }
+  b.stats.spmv_launches_timed = na;
+  b.stats.update_launches_timed = na;
+  b.stats.spmv_ms_avg = na ? (float)(sa / na) : 0.f;
+  b.stats.update_ms_avg = na ? (float)(su / na) : 0.f;
+  cudaEventElapsedTime(&b.stats.solve_ms, c.ev_t0, c.ev_t1);
+  b.stats.kernel_launches = launches;
+  c.launches += launches;
+  return cudaSuccess;
 }
 
-// iteration parity 0 reads p0 / writes p1, parity 1 the other way round
-cudaError_t launch_pcg_spmv(Batch& b, int parity, int max_iter, cudaStream_t st) {
-  const int ncta = (int)(b.NBR / kCtaRows);
-  if (!ncta) return cudaSuccess;
-  const PcgPtrs P = make_ptrs(b);
-  const double2* po = (const double2*)(parity ? b.p1 : b.p0);
-  double2* pn = (double2*)(parity ? b.p0 : b.p1);
-  pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(P, po, pn, parity, max_iter);
-  if (P.two_level) k_reduce_partials<<<b.ns, kT, 0, st>>>(b.cta_first, b.cta_count, b.sc.done, b.partA, b.sc.psumA);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_pcg_update(Batch& b, int parity, cudaStream_t st) {
-  const int ncta = (int)(b.NBR / kCtaRows);
-  if (!ncta) return cudaSuccess;
-  const PcgPtrs P = make_ptrs(b);
-  const double2* pn = (const double2*)(parity ? b.p0 : b.p1);
-  k_pcg_update<<<ncta, kT, 0, st>>>(P, pn, parity);
-  if (P.two_level) k_reduce_partials<<<b.ns, kT, 0, st>>>(b.cta_first, b.cta_count, b.sc.done, b.partB, b.sc.psumB);
-  return cudaGetLastError();
+void pcg_release(Ctx& c) {
+  for (auto& kv : c.pcg_graphs) cudaGraphExecDestroy(kv.second);
+  c.pcg_graphs.clear();
 }
 
 // ---------------------------------------------------------------------------
@@ -441,9 +627,12 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
   if (!ncta) return cudaSuccess;
   const unsigned g = (unsigned)((b.NBR + T - 1) / T);
   const int64_t v0 = b.vtx_off[s], v1 = b.vtx_off[s + 1];
+  PcgPtrs* dP = (PcgPtrs*)b.ctx->d_pcg_params;
+  k_store_params<<<1, 32, 0, st>>>(make_ptrs(b, 1 << 30), dP);
   k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc, b.cta_first, b.cta_count, b.partB);
+  k_compact_active<<<1, 1024, 0, st>>>(dP);
   k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (double2*)b.r, (double2*)b.p0);
-  pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(make_ptrs(b), (const double2*)b.p0, (double2*)b.p1, 0, 1 << 30);
+  pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(dP, 0);
   k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, (const double2*)b.q, d_y);
   return cudaGetLastError();
 }

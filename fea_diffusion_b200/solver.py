@@ -97,10 +97,10 @@ class BatchResult:
 class Context:
     """One fea_ctx: a GPU and a stream.  Not thread-safe; use one per host thread."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, priority: int = 0):
         self.lib = _capi.load_library()
         h = C.c_void_p()
-        rc = self.lib.fea_ctx_create(int(device), C.byref(h))
+        rc = self.lib.fea_ctx_create_prio(int(device), int(priority), C.byref(h))
         if rc != 0:
             raise FeaError(rc, "fea_ctx_create(device=%d) failed (no CUDA device?)" % device)
         self.h = h

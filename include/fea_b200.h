@@ -105,6 +105,9 @@ typedef struct fea_solve_stats {
 /* ---- library / context -------------------------------------------------- */
 int  fea_version(int* major, int* minor);
 int  fea_ctx_create(int device, fea_ctx** out);
+/* same, with a CUDA stream priority (0 = default, negative = higher): several contexts on one
+ * GPU let the tail of one batch overlap the bulk of the next; distinct priorities stagger them */
+int  fea_ctx_create_prio(int device, int priority, fea_ctx** out);
 int  fea_ctx_destroy(fea_ctx* ctx);
 const char* fea_last_error(const fea_ctx* ctx);
 /* pinned host memory for zero-staging uploads/downloads (optional) */
