@@ -18,12 +18,12 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 EXPORTS = [
     "fea_version", "fea_ctx_create", "fea_ctx_create_prio", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
-    "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
+    "fea_ctx_wait_ctx", "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
-    "fea_batch_download_images", "fea_batch_get_info", "fea_batch_get_solve_stats",
+    "fea_batch_download_images", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
     "fea_batch_get_timed_launches",
     "fea_batch_sample_sizes", "fea_batch_get_conn", "fea_batch_get_element_stiffness",
-    "fea_batch_get_csr", "fea_batch_spmv", "fea_solve_batch",
+    "fea_batch_get_csr", "fea_batch_spmv", "fea_rasterize_fields", "fea_solve_batch",
 ]
 
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "CUDA_ERROR", 3: "OUT_OF_MEMORY", 4: "BAD_STATE", 5: "MESH_ERROR"}
@@ -87,6 +87,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_ctx_create": (C.c_int, [C.c_int, C.POINTER(P)]),
         "fea_ctx_create_prio": (C.c_int, [C.c_int, C.c_int, C.POINTER(P)]),
         "fea_ctx_destroy": (C.c_int, [P]),
+        "fea_ctx_wait_ctx": (C.c_int, [P, P]),
         "fea_last_error": (C.c_char_p, [P]),
         "fea_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
         "fea_host_free": (C.c_int, [P, P]),
@@ -109,6 +110,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_get_element_stiffness": (C.c_int, [P, P]),
         "fea_batch_get_csr": (C.c_int, [P, I32, P, P, P]),
         "fea_batch_spmv": (C.c_int, [P, I32, P, P]),
+        "fea_batch_cell_strain_stress": (C.c_int, [P, I32, P, P]),
+        "fea_rasterize_fields": (C.c_int, [P, P, C.c_int64, P, C.c_int64, I32, P, I32, I32, P, P, I32, P]),
         "fea_solve_batch": (C.c_int, [P, C.POINTER(BatchDesc), F64, I32, I32, P, F64, P, P, P, P, P, P,
                                       C.POINTER(SolveStats)]),
     }

@@ -14,6 +14,7 @@ using namespace fea;
 struct fea_ctx {
   Ctx c;
   cudaEvent_t ev_user[8] = {};
+  cudaEvent_t ev_join = nullptr;
 };
 struct fea_batch {
   Batch b;
@@ -120,6 +121,7 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   cudaEventCreate(&ctx->c.ev_t0);
   cudaEventCreate(&ctx->c.ev_t1);
   for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   ctx->c.events.resize(3 * kMaxTimed);
   for (auto& ev : ctx->c.events) cudaEventCreate(&ev);
   *out = ctx;
@@ -137,6 +139,7 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaEventDestroy(ctx->c.ev_t0);
   cudaEventDestroy(ctx->c.ev_t1);
   for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
+  cudaEventDestroy(ctx->ev_join);
   cudaFreeHost(ctx->c.h_flag);
   cudaFree(ctx->c.d_pcg_params);
   cudaStreamDestroy(ctx->c.stream);
@@ -174,6 +177,15 @@ int fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t a, int32_t b, float* ms) {
   CK(ctx, cudaSetDevice(ctx->c.device));
   CK(ctx, cudaEventSynchronize(ctx->ev_user[b]));
   CK(ctx, cudaEventElapsedTime(ms, ctx->ev_user[a], ctx->ev_user[b]));
+  return FEA_OK;
+}
+int fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other) {
+  if (!ctx || !other) return FEA_BAD_ARG;
+  if (ctx == other) return FEA_OK;
+  if (ctx->c.device != other->c.device) return fail(ctx, FEA_BAD_ARG, "contexts are on different devices");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaEventRecord(other->ev_join, other->c.stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->c.stream, other->ev_join, 0));
   return FEA_OK;
 }
 int fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out) {
@@ -397,6 +409,26 @@ int fea_batch_download(fea_batch* hb, double* u, double* ranges, int32_t* iters,
   return FEA_OK;
 }
 
+int fea_batch_cell_strain_stress(fea_batch* hb, int32_t stress_region, double* strain, double* stress) {
+  if (!hb || (!strain && !stress)) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_cell_strain_stress before fea_batch_solve");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  double* d = nullptr;
+  const size_t n = (size_t)std::max<int64_t>(1, b.NC * 3);
+  CK(ctx, cudaMallocAsync((void**)&d, sizeof(double) * 2 * n, st));
+  cudaError_t e = launch_cell_strain_stress(b, stress_region, d, d + n);
+  if (e == cudaSuccess && strain) e = cudaMemcpyAsync(strain, d, sizeof(double) * 3 * b.NC, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && stress) e = cudaMemcpyAsync(stress, d + n, sizeof(double) * 3 * b.NC, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(d, st);
+  ctx->c.launches += 1;
+  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_cell_strain_stress", e);
+  return FEA_OK;
+}
+
 int fea_batch_download_images(fea_batch* hb, uint8_t* images) {
   if (!hb || !images) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
@@ -562,6 +594,47 @@ int fea_batch_spmv(fea_batch* hb, int32_t s, const double* x, double* y) {
   cudaFreeAsync(dx, st);
   cudaFreeAsync(dy, st);
   b.solved = false;  // solver vectors were overwritten
+  return FEA_OK;
+}
+
+int fea_rasterize_fields(fea_ctx* ctx, const double* xy, int64_t n_v, const int32_t* conn, int64_t n_cell,
+                         int32_t nodes_per_cell, const double* fields, int32_t n_fields, int32_t cell_fields,
+                         const double* clim, const double* affine, int32_t size, uint8_t* images) {
+  if (!ctx) return FEA_BAD_ARG;
+  if (!xy || !conn || !fields || !clim || !affine || !images) return fail(ctx, FEA_BAD_ARG, "null array");
+  if (nodes_per_cell != 3 && nodes_per_cell != 4) return fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
+  if (n_v < 1 || n_cell < 0 || n_fields < 1 || size < 1 || size > 8192 || n_v >= (1LL << 30))
+    return fail(ctx, FEA_BAD_ARG, "size out of range");
+  for (int64_t i = 0; i < n_cell * nodes_per_cell; ++i)
+    if (conn[i] < 0 || conn[i] >= n_v) return fail(ctx, FEA_MESH_ERROR, "connectivity index out of range");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  const int64_t per = (int64_t)size * size;
+  const size_t b_xy = sizeof(double) * 2 * n_v, b_cn = sizeof(int32_t) * n_cell * nodes_per_cell,
+               b_f = sizeof(double) * n_fields * (cell_fields ? std::max<int64_t>(n_cell, 1) : n_v), b_img = (size_t)n_fields * per;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_xy = 0, o_cn = o_xy + up(b_xy), o_f = o_cn + up(b_cn), o_cl = o_f + up(b_f),
+               o_af = o_cl + up(sizeof(double) * 2 * n_fields), o_co = o_af + 256, o_ow = o_co + 256,
+               o_im = o_ow + up(sizeof(int32_t) * per), total = o_im + up(b_img);
+  char* d = nullptr;
+  CK(ctx, cudaMallocAsync((void**)&d, total, st));
+  const int64_t h_off[2] = {0, n_cell};
+  cudaError_t e = cudaMemcpyAsync(d + o_xy, xy, b_xy, cudaMemcpyHostToDevice, st);
+#define A(call) if (e == cudaSuccess) e = (call)
+  if (b_cn) A(cudaMemcpyAsync(d + o_cn, conn, b_cn, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(d + o_f, fields, b_f, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(d + o_cl, clim, sizeof(double) * 2 * n_fields, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(d + o_af, affine, sizeof(double) * 4, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(d + o_co, h_off, sizeof(h_off), cudaMemcpyHostToDevice, st));
+  A(launch_raster_fields(st, nodes_per_cell, n_v, n_cell, (const int32_t*)(d + o_cn), (const double*)(d + o_xy),
+                         (const double*)(d + o_af), (const int64_t*)(d + o_co), size, (int32_t*)(d + o_ow),
+                         (const double*)(d + o_f), n_fields, cell_fields ? 1 : 0, (const double*)(d + o_cl), (uint8_t*)(d + o_im)));
+  A(cudaMemcpyAsync(images, d + o_im, b_img, cudaMemcpyDeviceToHost, st));
+  A(cudaStreamSynchronize(st));
+#undef A
+  cudaFreeAsync(d, st);
+  ctx->c.launches += 3;
+  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_rasterize_fields", e);
   return FEA_OK;
 }
 

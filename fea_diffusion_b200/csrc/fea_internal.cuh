@@ -129,6 +129,7 @@ cudaError_t launch_setup(Batch& b, const int8_t* d_cell_region_local, const int3
 cudaError_t launch_topology_counts(Batch& b);                 // incidence + adjacency counts
 cudaError_t launch_topology_fill(Batch& b);                   // adjacency fill
 cudaError_t launch_element_stiffness(Batch& b);
+cudaError_t launch_cell_strain_stress(Batch& b, int stress_region, double* d_strain, double* d_stress);
 cudaError_t launch_sell_lengths(Batch& b);                    // slice_len + slice_ptr
 cudaError_t launch_sell_fill(Batch& b);                       // dscale, val, col
 cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d_indices,
@@ -139,6 +140,11 @@ void pcg_release(Ctx& c);                                     // destroys the ca
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);
+// n_fields vertex-scalar images of one mesh; cell_off2 = device {0, n_cell}
+cudaError_t launch_raster_fields(cudaStream_t st, int npc, int64_t n_v, int64_t n_cell, const int32_t* conn,
+                                 const double* xy, const double* affine, const int64_t* cell_off2, int size,
+                                 int32_t* owner, const double* fields, int n_fields, int cell_fields,
+                                 const double* clim, uint8_t* images);
 
 // scans (device-wide, deterministic)
 cudaError_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tmp,

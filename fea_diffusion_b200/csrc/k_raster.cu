@@ -125,6 +125,62 @@ __global__ void k_raster_shade(int ns, int size, const int64_t* __restrict__ cel
   images[((int64_t)s * 2 + 1) * per + lp] = g1;
 }
 
+// Generic scalar fields of ONE mesh -- per vertex (region flags, the constant "1" field of
+// input.png: reference fea_analysis.py:472-524) or per cell (cauchy_strain / cauchy_stress
+// components, :541-549): field f is normalised by clim[f] and mapped like above.
+template <int NPC>
+__global__ void k_raster_shade_fields(int size, const int32_t* __restrict__ conn, const double* __restrict__ xy,
+                                      const double* __restrict__ affine, const int32_t* __restrict__ owner,
+                                      const double* __restrict__ fields, int64_t n_per_field, int n_fields,
+                                      int cell_fields, const double* __restrict__ clim,
+                                      uint8_t* __restrict__ images) {
+  constexpr int SUB = (NPC == 3) ? 1 : 2;
+  const int64_t lp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)size * size;
+  if (lp >= per) return;
+  const int j = (int)(lp / size), i = (int)(lp - (int64_t)j * size);
+  const int32_t o = owner[lp];
+  if (o == 0x7fffffff) {
+    for (int f = 0; f < n_fields; ++f) images[(int64_t)f * per + lp] = 255;
+    return;
+  }
+  Tri t;
+  int32_t vid[3];
+  load_tri<NPC>(o / SUB, o % SUB, conn, xy, affine, t, vid);
+  double w[3], a2;
+  bary(t, (double)i + 0.5, (double)j + 0.5, w, &a2);
+  for (int f = 0; f < n_fields; ++f) {
+    const double* __restrict__ fv = fields + (int64_t)f * n_per_field;
+    const double val = cell_fields ? fv[o / SUB]
+                                   : __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(w[0], fv[vid[0]]), __dmul_rn(w[1], fv[vid[1]])),
+                                                         __dmul_rn(w[2], fv[vid[2]])), a2);
+    const double vmin = clim[2 * f], rng = __dsub_rn(clim[2 * f + 1], vmin);
+    double tt = 0.0;
+    if (rng > 0.0) tt = __ddiv_rn(__dsub_rn(val, vmin), rng);
+    tt = fmin(fmax(tt, 0.0), 1.0);
+    images[(int64_t)f * per + lp] = (uint8_t)(255.0 - fmin(floor(__dmul_rn(256.0, tt)), 255.0));
+  }
+}
+
+cudaError_t launch_raster_fields(cudaStream_t st, int npc, int64_t n_v, int64_t n_cell, const int32_t* conn,
+                                 const double* xy, const double* affine, const int64_t* cell_off2, int size,
+                                 int32_t* owner, const double* fields, int n_fields, int cell_fields,
+                                 const double* clim, uint8_t* images) {
+  const int T = 256;
+  const int64_t per = (int64_t)size * size;
+  k_owner_init<<<(unsigned)((per + T - 1) / T), T, 0, st>>>(per, owner);
+  const int64_t NT = n_cell * (npc == 3 ? 1 : 2);
+  if (NT) {
+    const unsigned g = (unsigned)((NT + T - 1) / T);
+    if (npc == 3) k_raster_cover<3><<<g, T, 0, st>>>(NT, cell_off2, 1, conn, xy, affine, size, owner);
+    else k_raster_cover<4><<<g, T, 0, st>>>(NT, cell_off2, 1, conn, xy, affine, size, owner);
+  }
+  const unsigned gp = (unsigned)((per + T - 1) / T);
+  if (npc == 3) k_raster_shade_fields<3><<<gp, T, 0, st>>>(size, conn, xy, affine, owner, fields, cell_fields ? n_cell : n_v, n_fields, cell_fields, clim, images);
+  else k_raster_shade_fields<4><<<gp, T, 0, st>>>(size, conn, xy, affine, owner, fields, cell_fields ? n_cell : n_v, n_fields, cell_fields, clim, images);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_raster(Batch& b, double value_scale) {
   cudaStream_t st = b.ctx->stream;
   const int T = 256;

@@ -9,16 +9,20 @@ Worker threads only make ctypes calls (the GIL is released inside them).
 from __future__ import annotations
 
 from concurrent.futures import ThreadPoolExecutor
-from typing import Callable, List, Sequence
+from typing import Callable, List, Optional, Sequence
 
 from .solver import Context
 
 
 class Pipeline:
-    def __init__(self, device: int = 0, n_streams: int = 2, staggered_priorities: bool = True):
+    def __init__(self, device: int = 0, n_streams: int = 2, staggered_priorities: bool = False,
+                 first: Optional[Context] = None):
+        """``first`` adopts an existing context as stream 0 (closed with the pipeline)."""
         self.device = device
-        self.ctxs: List[Context] = [Context(device, priority=(-i if staggered_priorities else 0))
-                                    for i in range(n_streams)]
+        self.ctxs: List[Context] = [first] if first is not None else []
+        while len(self.ctxs) < n_streams:
+            i = len(self.ctxs)
+            self.ctxs.append(Context(device, priority=(-i if staggered_priorities else 0)))
         self.pool = ThreadPoolExecutor(max_workers=n_streams)
 
     @property
@@ -44,6 +48,13 @@ class Pipeline:
         for f in futs:
             f.result()
         return out
+
+    def join_into(self, ctx: Context):
+        """Stream-order ``ctx`` after everything submitted so far on every stream of the pipeline
+        (so one CUDA event on ``ctx`` closes a region timed across all of them)."""
+        for c in self.ctxs:
+            if c is not ctx:
+                ctx.wait_for(c)
 
     def kernel_launches(self) -> int:
         return sum(c.kernel_launches() for c in self.ctxs)

@@ -136,6 +136,10 @@ class Context:
         self._check(self.lib.fea_ctx_event_elapsed_ms(self.h, int(start), int(stop), C.byref(ms)))
         return float(ms.value)
 
+    def wait_for(self, other: "Context"):
+        """Stream-order this context after everything submitted to ``other`` so far."""
+        self._check(self.lib.fea_ctx_wait_ctx(self.h, other.h))
+
     def kernel_launches(self) -> int:
         n = C.c_int64()
         self._check(self.lib.fea_ctx_kernel_launches(self.h, C.byref(n)))
@@ -150,6 +154,24 @@ class Context:
         self._pinned.append(p)
         buf = (C.c_char * max(count * dtype.itemsize, 1)).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def rasterize_fields(self, coors: np.ndarray, conn: np.ndarray, fields: np.ndarray, clim: np.ndarray,
+                         affine: np.ndarray, size: int, cell_fields: bool = False) -> np.ndarray:
+        """(n_fields, size, size) uint8 images of scalar fields of one mesh (fea_rasterize_fields):
+        per-vertex (region flags, the constant field of input.png) or per-cell (stress/strain)."""
+        coors = np.ascontiguousarray(coors, dtype=np.float64)
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        fields = np.ascontiguousarray(np.atleast_2d(fields), dtype=np.float64)
+        clim = np.ascontiguousarray(clim, dtype=np.float64).reshape(len(fields), 2)
+        affine = np.ascontiguousarray(affine, dtype=np.float64).reshape(4)
+        if fields.shape[1] != (len(conn) if cell_fields else len(coors)):
+            raise ValueError("fields must be (n_fields, n_vertices) or (n_fields, n_cells)")
+        out = np.empty((len(fields), int(size), int(size)), np.uint8)
+        self._check(self.lib.fea_rasterize_fields(self.h, ptr(coors), len(coors), ptr(conn), len(conn),
+                                                  conn.shape[1], ptr(fields), len(fields), int(bool(cell_fields)), ptr(clim),
+                                                  ptr(affine),
+                                                  int(size), ptr(out)))
+        return out
 
     def create_batch(self, packed: PackedBatch) -> "Batch":
         return Batch(self, packed)
@@ -227,6 +249,13 @@ class Batch:
             self.ctx._check(self.ctx.lib.fea_batch_download_images(self.h, ptr(r.images)))
         r.stats = self.stats()
         return r
+
+    def cell_strain_stress(self, stress_region: int = -1):
+        """(strain, stress), each (n_cells, 3): final-step cell averages (e11, e22, 2e12), D*strain."""
+        nc = len(self.packed.conn)
+        strain, stress = np.empty((nc, 3)), np.empty((nc, 3))
+        self.ctx._check(self.ctx.lib.fea_batch_cell_strain_stress(self.h, int(stress_region), ptr(strain), ptr(stress)))
+        return strain, stress
 
     def info(self) -> dict:
         i = BatchInfo()

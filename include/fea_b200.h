@@ -118,6 +118,9 @@ int  fea_ctx_synchronize(fea_ctx* ctx);
  * (slot in [0, 8)); elapsed is valid once the later event has completed. */
 int  fea_ctx_event_record(fea_ctx* ctx, int32_t slot);
 int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_stop, float* ms);
+/* work submitted to ctx after this call starts only once everything submitted to `other` so far
+ * has finished (same device): joins several contexts' streams for one event-timed region */
+int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
 /* number of kernels this context has launched so far (graph nodes included) */
 int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
 
@@ -150,6 +153,12 @@ int  fea_batch_destroy(fea_batch* b);
 int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
                         double* relres, int32_t* status);
 int  fea_batch_download_images(fea_batch* b, uint8_t* images);
+/* Final-step cell averages written into domain.<k>.vtk by the reference's post-process hook
+ * (ev_cauchy_strain / ev_cauchy_stress 'el_avg', fea_analysis.py:397-416): strain [n_cells*3] =
+ * (e11, e22, 2e12), stress [n_cells*3] = D * strain.  stress_region >= 0: material-table entry of
+ * the sample used for EVERY cell (the hook evaluates the single material named 'm' over Omega);
+ * -1: each cell's own D, zero for cells without stiffness.  Either pointer may be NULL. */
+int  fea_batch_cell_strain_stress(fea_batch* b, int32_t stress_region, double* strain, double* stress);
 int  fea_batch_get_info(fea_batch* b, fea_batch_info* out);
 int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
 /* CUDA-event durations of the SpMV / update launch that opens each chunk of 32 PCG iterations
@@ -170,6 +179,19 @@ int  fea_batch_get_csr(fea_batch* b, int32_t sample, int32_t* indptr, int32_t* i
                        double* data);
 /* y = K x for one sample through the product SpMV kernel (x, y over active DOFs, unscaled) */
 int  fea_batch_spmv(fea_batch* b, int32_t sample, const double* x, double* y);
+
+/* ---- scalar-field images of one mesh ----------------------------------------
+ * The point-scalar renders of FEAnalysis.save_input_image / save_region_images (reference
+ * fea_analysis.py:472-524: the constant field "1" and the 0/1 region flags of regions.vtk) and the
+ * cell-scalar renders of the stress/strain components (:541-549), same camera, coverage rule and
+ * 'binary' colour map as fea_batch_rasterize (A-16).
+ * fields [n_fields][n_v] (cell_fields = 0, interpolated) or [n_fields][n_cell] (cell_fields = 1,
+ * constant per cell); clim [n_fields][2] = (min, max) mapped to white..black;
+ * affine [4] as above; images [n_fields][size][size] uint8, background 255. */
+int  fea_rasterize_fields(fea_ctx* ctx, const double* xy, int64_t n_v, const int32_t* conn,
+                          int64_t n_cell, int32_t nodes_per_cell, const double* fields,
+                          int32_t n_fields, int32_t cell_fields, const double* clim,
+                          const double* affine, int32_t size, uint8_t* images);
 
 /* ---- one-call convenience: create + assemble + solve (+ rasterize) + download + destroy.
  * This is the host-buffer end-to-end path (the "e2e" number of bench.py). */

@@ -1,0 +1,146 @@
+"""The drop-in ``FEAnalysis`` / ``generate_data`` surface on the GPU, checked against the CPU oracle
+and the reference's committed text files."""
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import cases
+from fea_diffusion_b200 import imaging
+from fea_diffusion_b200.datagen import FEAnalysis, generate_data
+from fea_diffusion_b200.datagen.mesh_generator import write_medit
+from fea_diffusion_b200.datagen.vtk_io import read_vtk
+from fea_diffusion_b200.host import read_mesh
+from oracle import raster_oracle as ro
+from oracle.fea_oracle import OracleProblem
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def test_feanalysis_cantilever_files_and_fields(tmp_path, golden):
+    data_dir, cond_dir = str(tmp_path), str(tmp_path / "1")
+    os.makedirs(cond_dir)
+    write_medit(os.path.join(data_dir, "part.mesh"), golden["cantilever_coors"], golden["cantilever_conn"])
+    kw = dict(force_vertex_tags_magnitudes=[(4, (0, -1000))], force_edges_tags_magnitudes=[((3, 4), (120, 0))],
+              constraints_vertex_tags=[], constraints_edges_tags=[(1, 2)])
+    an = FEAnalysis("part.mesh", data_dir, cond_dir, num_steps=5, save_meshes=True, **kw)
+    assert an.initial_image_size == 747 and an.image_size == 747 and an.bounds == (0, 0, 747, 747)
+    assert an.calculate() is True
+    orc = OracleProblem(golden["cantilever_coors"], golden["cantilever_conn"], num_steps=5, **kw)
+    u = orc.solve("reference")
+    for k in range(5):
+        if k:
+            assert rel(an.displacement[k], u[k]) <= 1e-8
+        pts, cells, pd, cd = read_vtk(os.path.join(cond_dir, "domain.%d.vtk" % k))
+        assert np.array_equal(pd["u"][:, :2], an.displacement[k]) and np.all(pd["u"][:, 2] == 0)
+        assert np.array_equal(cells, orc.conn) and np.array_equal(pts[:, :2], orc.coors)
+        assert set(cd) == {"cauchy_strain", "cauchy_stress", "mat_id"}
+    # el_avg strain of a P1 cell = B u_e; checked against a direct numpy evaluation
+    co, cn, uf = orc.coors, orc.conn, an.displacement[-1]
+    x, y = co[cn, 0], co[cn, 1]
+    det = (x[:, 1] - x[:, 0]) * (y[:, 2] - y[:, 0]) - (x[:, 2] - x[:, 0]) * (y[:, 1] - y[:, 0])
+    gx = np.stack([y[:, 1] - y[:, 2], y[:, 2] - y[:, 0], y[:, 0] - y[:, 1]], 1) / det[:, None]
+    gy = np.stack([x[:, 2] - x[:, 1], x[:, 0] - x[:, 2], x[:, 1] - x[:, 0]], 1) / det[:, None]
+    ux, uy = uf[cn, 0], uf[cn, 1]
+    strain = np.stack([(gx * ux).sum(1), (gy * uy).sum(1), (gy * ux + gx * uy).sum(1)], 1)
+    assert np.abs(an.cell_strain - strain).max() <= 1e-12 * np.abs(strain).max()
+    D = an.setup.sample.D[0]
+    assert np.abs(an.cell_stress - strain @ D.T).max() <= 1e-12 * np.abs(strain @ D.T).max()
+    assert os.path.exists(os.path.join(cond_dir, "regions.vtk"))
+    _, _, rp, _ = read_vtk(os.path.join(cond_dir, "regions.vtk"))
+    assert set(rp) == {"Omega", "VertexForce0", "EdgeForce0", "EdgeConstraint0"}
+    assert int(rp["EdgeConstraint0"].sum()) == 21 and int(rp["VertexForce0"].sum()) == 1
+    assert open(os.path.join(cond_dir, "magnitudes.txt")).read() == \
+        "VertexForce0:(0, -1000)\nEdgeForce0:(%s, 0.0)\n" % repr(120 / 21)
+    # images: two-pass window sizing as generate.py:129-145 does it
+    out = os.path.join(data_dir, "outline.png")
+    an.save_input_image(out, outline=True, crop=False)
+    from fea_diffusion_b200.datagen.utils import find_image_bounds
+    l, t, r, b = find_image_bounds(out)
+    W2 = round(64 / (max(r - l, b - t) / an.initial_image_size))
+    an.update_image_size_or_bounds(image_size=W2)
+    an.save_input_image(out, outline=True, crop=False)
+    l, t, r, b = find_image_bounds(out)
+    lo, hi = (l, r) if r > b else (t, b)
+    an.update_image_size_or_bounds(bounds=(lo, lo, hi, hi))
+    assert (W2, (lo, lo, hi, hi)) == imaging.plate_window(an.setup.bbox(), 64)
+    an.save_input_image(os.path.join(data_dir, "input.png"))
+    an.save_region_images(os.path.join(cond_dir, "regions"))
+    an.save_output_images(os.path.join(cond_dir, "outputs"), save_displacement=True, save_stress=True, save_strain=False)
+    size = hi - lo
+    inp = np.array(Image.open(os.path.join(data_dir, "input.png")))
+    assert inp.shape == (size, size, 3) and (inp == 0).any() and (inp == 255).any()
+    lines = open(os.path.join(cond_dir, "ranges.txt")).read().splitlines()
+    assert len(lines) == 4 * 4 and lines[0].startswith("displacement_x_1:(") and lines[3].startswith("stress_y_1:(")
+    lo_hi = eval(lines[4 + 1].split(":", 1)[1])          # displacement_y_2
+    assert abs(lo_hi[0] - u[2][:, 1].min()) <= 1e-8 * abs(u[2][:, 1].min())
+    aff = imaging.crop_affine(an.setup.bbox(), W2, (lo, lo, hi, hi))
+    for c, name in enumerate(["displacement_x", "displacement_y"]):
+        img = np.array(Image.open(os.path.join(cond_dir, "outputs_%s.png" % name)))
+        assert img.shape == (size, size, 3) and np.array_equal(img[:, :, 0], img[:, :, 2])
+        ref = ro.rasterize_scalar(orc.coors, orc.conn, u[1][:, c], size, aff)
+        assert np.abs(ref.astype(int) - img[:, :, 0].astype(int)).max() <= 1
+    assert Image.open(os.path.join(cond_dir, "regions_EdgeConstraint0.png")).size == (size, size)
+    for name in ("stress_x", "stress_y"):
+        assert os.path.exists(os.path.join(cond_dir, "outputs_%s.png" % name))
+    # the 0/1 region flag decays over one 0.01-wide cell: sub-pixel at 64 px, a dark band at 512 px
+    an.update_image_size_or_bounds(image_size=512, bounds=(0, 0, 512, 512))
+    an.save_region_images(os.path.join(cond_dir, "big"))
+    reg = np.array(Image.open(os.path.join(cond_dir, "big_EdgeConstraint0.png")))[:, :, 0]
+    assert reg.shape == (512, 512) and reg[:, :128].min() < 64 and reg[:, 128:].min() == 255
+    frc = np.array(Image.open(os.path.join(cond_dir, "big_EdgeForce0.png")))[:, :, 0]
+    assert frc[:, 384:].min() < 64 and frc[:, :384].min() == 255          # edge (3, 4) is the right edge
+    an.clear_condition_dir()
+    assert os.listdir(cond_dir) == []
+
+
+def test_feanalysis_text_files_match_the_committed_composite_condition(tmp_path, golden_meta):
+    """applications/composite/{magnitudes,materials}.txt (reference) for the notebook's condition;
+    that condition floats (F4), which strict mode reports instead of writing solver noise."""
+    co, cn, kw = cases.composite_args(well_posed=False)
+    kw = dict(force_edges_tags_magnitudes=[], constraints_edges_tags=[], **kw)   # required positionals
+    data_dir, cond_dir = str(tmp_path), str(tmp_path / "c")
+    os.makedirs(cond_dir)
+    write_medit(os.path.join(data_dir, "part.mesh"), co, cn)
+    an = FEAnalysis("part.mesh", data_dir, cond_dir, num_steps=2, max_iter=2000, **kw)
+    assert open(os.path.join(cond_dir, "magnitudes.txt")).read() == golden_meta["composite_magnitudes"]
+    assert open(os.path.join(cond_dir, "materials.txt")).read() == golden_meta["composite_materials"]
+    assert an.calculate() is False
+    lenient = FEAnalysis("part.mesh", data_dir, cond_dir, num_steps=2, max_iter=2000, strict=False, **kw)
+    assert lenient.calculate() is True and np.isfinite(lenient.displacement).all()
+
+
+def test_generate_data_tree(tmp_path):
+    """generate_data (reference datagen/generate.py) end to end: directory tree and file
+    contents the training set reader expects (model/diffusion.py:134-141, 174-217, 359-378)."""
+    d = str(tmp_path / "data")
+    generate_data(data_dir=d, image_size=64, num_plates=2, conditions_per_plate=2, mesh_size=4e-2,
+                  num_steps_per_condition=5, save_meshes=True, random_seed=11, verbose=False)
+    assert sorted(os.listdir(d)) == ["1", "2", "part.mesh"]
+    co, cn = read_mesh(os.path.join(d, "part.mesh"))   # mesh of the last plate
+    for plate in ("1", "2"):
+        pd = os.path.join(d, plate)
+        assert {"1", "2", "input.png", "outline.png"} <= set(os.listdir(pd))
+        size = Image.open(os.path.join(pd, "input.png")).size
+        assert abs(size[0] - 64) <= 2 and size[0] == size[1]
+        for cond in ("1", "2"):
+            cd = os.path.join(pd, cond)
+            files = set(os.listdir(cd))
+            assert {"outputs_displacement_x.png", "outputs_displacement_y.png", "magnitudes.txt", "materials.txt",
+                    "ranges.txt", "regions.vtk"} <= files
+            assert {"domain.%d.vtk" % k for k in range(5)} <= files
+            assert any(f.startswith("regions_MaterialRegion") for f in files)
+            assert Image.open(os.path.join(cd, "outputs_displacement_x.png")).size == size
+            lines = open(os.path.join(cd, "ranges.txt")).read().splitlines()
+            assert [l.split(":")[0] for l in lines] == ["displacement_%s_%d" % (c, k) for k in range(1, 5) for c in "xy"]
+            _, _, p4, _ = read_vtk(os.path.join(cd, "domain.4.vtk"))
+            _, _, p1, _ = read_vtk(os.path.join(cd, "domain.1.vtk"))
+            assert np.allclose(p1["u"], 0.25 * p4["u"], rtol=1e-14, atol=0)
+            lo, hi = eval(lines[-2].split(":", 1)[1])
+            assert lo == p4["u"][:, 0].min() and hi == p4["u"][:, 0].max()
+    assert len(co) == len(p4["u"])
