@@ -322,14 +322,12 @@ int fea_batch_assemble(fea_batch* hb) {
   b.max_row_blocks = h_err[1];
   CK(ctx, dalloc(b, &b.adj, b.n_adj));
   CK(ctx, launch_topology_fill(b));
-  CK(ctx, dalloc(b, &b.val, b.n_blocks * 2));
+  CK(ctx, dalloc(b, &b.val, b.n_blocks * 4));
   CK(ctx, dalloc(b, &b.col, b.n_blocks));
   CK(ctx, dalloc(b, &b.dscale, b.NBR * 2));
   CK(ctx, dalloc(b, &b.dcoup, b.NBR));
   CK(ctx, dalloc(b, &b.x, b.NBR * 2));
-  CK(ctx, dalloc(b, &b.r, b.NBR * 2));
-  CK(ctx, dalloc(b, &b.p0, b.NBR * 2));
-  CK(ctx, dalloc(b, &b.p1, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.rp, b.NBR * 4));
   CK(ctx, dalloc(b, &b.q, b.NBR * 2));
   const int64_t ncta = b.NBR / kCtaRows;
   CK(ctx, dalloc(b, &b.active_cta, 4 * ncta));  // int4 entries

@@ -100,13 +100,14 @@ struct Batch {
   int32_t* slice_len = nullptr;  // [n_slices]
   int64_t* slice_ptr = nullptr;  // [n_slices+1] in block entries
   int64_t n_blocks = 0;
-  double2* val = nullptr;        // [n_blocks*2]  per (slice,j): 32 top rows then 32 bottom rows
+  double* val = nullptr;         // [n_blocks*4]  one 32-byte block (k00,k01,k10,k11) per entry
   int32_t* col = nullptr;        // [n_blocks]
   double* dscale = nullptr;      // [NBR*2] 1/sqrt(diag)
   double* dcoup = nullptr;       // [NBR] scaled x-y coupling of the diagonal block
   int32_t max_row_blocks = 0;
-  // solver vectors [NBR*2]
-  double *x = nullptr, *r = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr;
+  // solver vectors: x, q [NBR*2]; rp [NBR*4] = one 32-byte record (r.x, r.y, p.x, p.y) per block
+  // row, so that a neighbour's residual and search direction arrive with ONE 256-bit gather
+  double *x = nullptr, *rp = nullptr, *q = nullptr;
   double *partA = nullptr, *partB = nullptr;  // [NBR/kCtaRows]
   SysScalars sc{};
   double* rz_last = nullptr;   // [ns] r.z at exit
@@ -168,10 +169,21 @@ __device__ __forceinline__ int warp_max_i(int v) {
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// streaming 16-byte load that does not allocate in L1 (matrix values, read once per kernel)
-__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
-  double2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+// 32-byte aligned quadruple: a 2x2 block (k00,k01,k10,k11) or an (r.x, r.y, p.x, p.y) record;
+// sm_100 moves it with one 256-bit load/store (LDG.E.256 / STG.E.256)
+struct __align__(32) d4 {
+  double x, y, z, w;
+};
+// streaming 32-byte load that does not allocate in L1 (matrix values, read once per kernel)
+__device__ __forceinline__ d4 ld_stream_d4(const d4* p) {
+  d4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+// read-only 32-byte load through L1 (vector records gathered by several rows of a CTA)
+__device__ __forceinline__ d4 ld_nc_d4(const d4* p) {
+  d4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ int ld_stream_i32(const int* p) {

@@ -5,10 +5,9 @@
 // vertex are always eliminated together, reference datagen/fea_analysis.py:367).  32 block rows
 // form a slice; a slice stores slice_len 2x2 blocks per row, column-major over the slice:
 //   entry e = slice_ptr[slice] + j*32 + lane
-//   val[2*(slice_ptr + j*32) + lane]       = (k00, k01)   top rows of the 32 blocks
-//   val[2*(slice_ptr + j*32) + 32 + lane]  = (k10, k11)   bottom rows
+//   val[e] = (k00, k01, k10, k11)   one 32-byte record per block
 //   col[e] = block column (global block row id of the neighbour vertex)
-// so a warp reads 512 contiguous bytes per load instruction.  Values are stored scaled:
+// so a warp reads 1024 contiguous bytes with one 256-bit load instruction per lane.  Values are stored scaled:
 //   Khat = S K S,  S = diag(1/sqrt(K_ii))  ->  CG on Khat == Jacobi-PCG on K.
 // Only OFF-diagonal blocks live in the SELL arrays.  After scaling the diagonal block of a
 // vertex is [[1, a], [a, 1]] (unit diagonal up to one rounding of s*K_ii*s, taken as exactly 1),
@@ -105,7 +104,7 @@ __global__ void k_sell_fill(int64_t NBR, const int32_t* __restrict__ vertex_of_r
                             const int32_t* __restrict__ inc, const int32_t* __restrict__ conn,
                             const double* __restrict__ ke, const double* __restrict__ dscale,
                             const int32_t* __restrict__ slice_len, const int64_t* __restrict__ slice_ptr,
-                            double2* __restrict__ val, int32_t* __restrict__ col, double* __restrict__ dcoup) {
+                            d4* __restrict__ val, int32_t* __restrict__ col, double* __restrict__ dcoup) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= NBR) return;
   const int lane = threadIdx.x & 31;
@@ -134,15 +133,20 @@ __global__ void k_sell_fill(int64_t NBR, const int32_t* __restrict__ vertex_of_r
     const int wr = row_of_vertex[w];
     const double t0 = dscale[2 * (int64_t)wr], t1 = dscale[2 * (int64_t)wr + 1];
     const int64_t e = base + (int64_t)j * 32;
-    val[2 * e + lane] = make_double2(s0 * k[0] * t0, s0 * k[1] * t1);
-    val[2 * e + 32 + lane] = make_double2(s1 * k[2] * t0, s1 * k[3] * t1);
+    d4 blk;
+    blk.x = s0 * k[0] * t0;
+    blk.y = s0 * k[1] * t1;
+    blk.z = s1 * k[2] * t0;
+    blk.w = s1 * k[3] * t1;
+    val[e + lane] = blk;
     col[e + lane] = wr;
     ++j;
   }
   for (; j < L; ++j) {  // slice padding: zero block pointing at the own row
     const int64_t e = base + (int64_t)j * 32;
-    val[2 * e + lane] = make_double2(0.0, 0.0);
-    val[2 * e + 32 + lane] = make_double2(0.0, 0.0);
+    d4 zero;
+    zero.x = zero.y = zero.z = zero.w = 0.0;
+    val[e + lane] = zero;
     col[e + lane] = (int32_t)row;
   }
   dcoup[row] = coup;
@@ -156,11 +160,11 @@ cudaError_t launch_sell_fill(Batch& b) {
   if (b.npc == 3) {
     k_diag_scale<3><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vsample, b.inc_ptr, b.inc, b.ke, b.dscale, b.empty);
     k_sell_fill<3><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.row_of_vertex, b.adj_ptr, b.adj, b.inc_ptr, b.inc,
-                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col, b.dcoup);
+                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, (d4*)b.val, b.col, b.dcoup);
   } else {
     k_diag_scale<4><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vsample, b.inc_ptr, b.inc, b.ke, b.dscale, b.empty);
     k_sell_fill<4><<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.row_of_vertex, b.adj_ptr, b.adj, b.inc_ptr, b.inc,
-                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, b.val, b.col, b.dcoup);
+                                    b.conn, b.ke, b.dscale, b.slice_len, b.slice_ptr, (d4*)b.val, b.col, b.dcoup);
   }
   return cudaGetLastError();
 }

@@ -12,7 +12,13 @@
 //                                         separate p-update pass over HBM)
 //           partA[cta] = p . q over the CTA's rows
 //   update: pq   = sum of the p.q partials;  alpha = rz / pq
-//           x += alpha p;  r -= alpha q;  partB[cta] = r . r over the CTA's rows
+//           p = r + beta * p_old (same expression, same bits);  x += alpha p;  r -= alpha q
+//           partB[cta] = r . r over the CTA's rows
+//
+// r and p live interleaved in one array of 32-byte records (r.x, r.y, p.x, p.y): the SpMV fetches
+// a neighbour's residual and previous direction with ONE 256-bit gather that uses a whole 32-byte
+// sector, and a 2x2 matrix block is one 256-bit load as well.  Only the update kernel writes the
+// records (its own rows), so the SpMV reads them without any ping-pong buffer.
 //
 // Every CTA (128 block rows) belongs to exactly one system.  Dot products never use atomics or
 // fences: a kernel leaves one partial per CTA and every warp of the *next* kernel re-adds the
@@ -60,13 +66,12 @@ struct PcgPtrs {
   const int32_t* cta_count;
   const int32_t* slice_len;
   const int64_t* slice_ptr;
-  const double2* val;
+  const d4* val;
   const int32_t* col;
   const double* dcoup;
   double2* x;
-  double2* r;
+  d4* rp;            // (r.x, r.y, p.x, p.y) per block row; p = direction of the PREVIOUS iteration
   double2* q;
-  double2* p[2];     // iteration parity 0 reads p[0] / writes p[1], parity 1 the other way round
   double* partA;
   double* partB;
   SysScalars sc;
@@ -115,47 +120,37 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
   const int64_t slice = row >> 5;
   const int L = P.slice_len[slice];
   const int64_t base = P.slice_ptr[slice];
-  const double2* __restrict__ vt = P.val + 2 * base + lane;
+  const d4* __restrict__ vt = P.val + base + lane;
   const int32_t* __restrict__ cp = P.col + base + lane;
-  const double2* __restrict__ r = P.r;
-  const double2* __restrict__ p_old = P.p[parity];
+  const d4* __restrict__ rp = P.rp;
   // own row: p_i and the diagonal block [[1, a], [a, 1]]
-  const double2 ri = __ldg(r + row);
-  const double2 pi = __ldg(p_old + row);
+  const d4 own = ld_nc_d4(rp + row);
   const double dc = __ldg(P.dcoup + row);
-  const double2 pn = make_double2(fma(beta, pi.x, ri.x), fma(beta, pi.y, ri.y));
+  const double2 pn = make_double2(fma(beta, own.z, own.x), fma(beta, own.w, own.y));
   double a0 = fma(dc, pn.y, pn.x), a1 = fma(dc, pn.x, pn.y);
 #pragma unroll 1
   for (int j0 = 0; j0 < L; j0 += U) {
     int c[U];
-    double2 t[U], b[U], rj[U], pj[U];
+    d4 k[U], g[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) c[u] = (j0 + u < L) ? ld_stream_i32(cp + (j0 + u) * 32) : (int)row;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      t[u] = make_double2(0.0, 0.0);
-      b[u] = make_double2(0.0, 0.0);
-      if (j0 + u < L) {
-        t[u] = ld_stream_f64x2(vt + (j0 + u) * 64);
-        b[u] = ld_stream_f64x2(vt + (j0 + u) * 64 + 32);
-      }
+      k[u].x = k[u].y = k[u].z = k[u].w = 0.0;
+      if (j0 + u < L) k[u] = ld_stream_d4(vt + (j0 + u) * 32);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      rj[u] = __ldg(r + c[u]);
-      pj[u] = __ldg(p_old + c[u]);
-    }
+    for (int u = 0; u < U; ++u) g[u] = ld_nc_d4(rp + c[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double px = fma(beta, pj[u].x, rj[u].x);
-      const double py = fma(beta, pj[u].y, rj[u].y);
-      a0 = fma(t[u].x, px, a0);
-      a0 = fma(t[u].y, py, a0);
-      a1 = fma(b[u].x, px, a1);
-      a1 = fma(b[u].y, py, a1);
+      const double px = fma(beta, g[u].z, g[u].x);
+      const double py = fma(beta, g[u].w, g[u].y);
+      a0 = fma(k[u].x, px, a0);
+      a0 = fma(k[u].y, py, a0);
+      a1 = fma(k[u].z, px, a1);
+      a1 = fma(k[u].w, py, a1);
     }
   }
-  P.p[parity ^ 1][row] = pn;
   P.q[row] = make_double2(a0, a1);
   const double part = cta_sum(fma(pn.x, a0, pn.y * a1), sm);
   if (threadIdx.x == 0) P.partA[cta] = part;
@@ -163,16 +158,19 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
 
 typedef void (*spmv_fn)(const PcgPtrs*, int);
 static spmv_fn pick_spmv(int variant) {
-  switch (variant) {
-    case 1: return k_pcg_spmv<1, 1>;
-    case 2: return k_pcg_spmv<2, 1>;
-    case 3: return k_pcg_spmv<3, 1>;
-    case 4: return k_pcg_spmv<4, 1>;
-    case 12: return k_pcg_spmv<2, 12>;
-    case 16: return k_pcg_spmv<2, 16>;
-    case 14: return k_pcg_spmv<4, 8>;
-    case 13: return k_pcg_spmv<3, 8>;
-    default: return k_pcg_spmv<2, 16>;
+  switch (variant) {  // FEA_SPMV_VARIANT = 100 * U + MINB  (tuning knob)
+    case 108: return k_pcg_spmv<1, 8>;
+    case 112: return k_pcg_spmv<1, 12>;
+    case 116: return k_pcg_spmv<1, 16>;
+    case 208: return k_pcg_spmv<2, 8>;
+    case 210: return k_pcg_spmv<2, 10>;
+    case 212: return k_pcg_spmv<2, 12>;
+    case 216: return k_pcg_spmv<2, 16>;
+    case 308: return k_pcg_spmv<3, 8>;
+    case 310: return k_pcg_spmv<3, 10>;
+    case 408: return k_pcg_spmv<4, 8>;
+    case 406: return k_pcg_spmv<4, 6>;
+    default: return k_pcg_spmv<1, 16>;
   }
 }
 
@@ -193,19 +191,22 @@ __global__ void __launch_bounds__(kT) k_pcg_update(const PcgPtrs* __restrict__ P
     }
     return;
   }
-  const double alpha = P.sc.rz[parity][s] / pq;
+  const double rz = P.sc.rz[parity][s];
+  const double alpha = rz / pq;
+  const double beta = rz / P.sc.rz[parity ^ 1][s];  // the value the SpMV of this iteration used
   const int64_t row = (int64_t)cta * kT + threadIdx.x;
-  const double2 pv = P.p[parity ^ 1][row];
+  d4 rec = P.rp[row];
   const double2 qv = P.q[row];
   double2 xv = P.x[row];
-  double2 rv = P.r[row];
-  xv.x = fma(alpha, pv.x, xv.x);
-  xv.y = fma(alpha, pv.y, xv.y);
-  rv.x = fma(-alpha, qv.x, rv.x);
-  rv.y = fma(-alpha, qv.y, rv.y);
+  rec.z = fma(beta, rec.z, rec.x);   // p of this iteration, bit-identical to the SpMV's
+  rec.w = fma(beta, rec.w, rec.y);
+  xv.x = fma(alpha, rec.z, xv.x);
+  xv.y = fma(alpha, rec.w, xv.y);
+  rec.x = fma(-alpha, qv.x, rec.x);
+  rec.y = fma(-alpha, qv.y, rec.y);
   P.x[row] = xv;
-  P.r[row] = rv;
-  const double part = cta_sum(fma(rv.x, rv.x, rv.y * rv.y), sm);
+  P.rp[row] = rec;
+  const double part = cta_sum(fma(rec.x, rec.x, rec.y * rec.y), sm);
   if (threadIdx.x == 0) {
     P.partB[cta] = part;
     if (leader) P.sc.iters[s] += 1;
@@ -281,11 +282,13 @@ __global__ void __launch_bounds__(kT) k_pcg_init_vectors(const PcgPtrs* __restri
   double2 b = make_double2(0.0, 0.0);
   if (v >= 0) b = make_double2(dscale[2 * row] * rhs[2 * (int64_t)v], dscale[2 * row + 1] * rhs[2 * (int64_t)v + 1]);
   const double2 z = make_double2(0.0, 0.0);
+  d4 rec;
+  rec.x = b.x;
+  rec.y = b.y;
+  rec.z = rec.w = 0.0;
   P.x[row] = z;
-  P.r[row] = b;
+  P.rp[row] = rec;
   P.q[row] = z;
-  P.p[0][row] = z;
-  P.p[1][row] = z;
   const double part = cta_sum(fma(b.x, b.x, b.y * b.y), sm);
   if (threadIdx.x == 0) P.partB[blockIdx.x] = part;
 }
@@ -321,14 +324,12 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   P.cta_count = b.cta_count;
   P.slice_len = b.slice_len;
   P.slice_ptr = b.slice_ptr;
-  P.val = b.val;
+  P.val = (const d4*)b.val;
   P.col = b.col;
   P.dcoup = b.dcoup;
   P.x = (double2*)b.x;
-  P.r = (double2*)b.r;
+  P.rp = (d4*)b.rp;
   P.q = (double2*)b.q;
-  P.p[0] = (double2*)b.p0;
-  P.p[1] = (double2*)b.p1;
   P.partA = b.partA;
   P.partB = b.partB;
   P.sc = b.sc;
@@ -579,7 +580,7 @@ cudaError_t launch_finalize(Batch& b) {
 __global__ void k_spmv_load(int64_t NBR, const int32_t* __restrict__ vertex_of_row,
                             const int32_t* __restrict__ vrank, int64_t v0, int64_t v1,
                             const double* __restrict__ dscale, const double* __restrict__ xin,
-                            double2* __restrict__ r, double2* __restrict__ p0) {
+                            d4* __restrict__ rp) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= NBR) return;
   const int v = vertex_of_row[row];
@@ -589,8 +590,11 @@ __global__ void k_spmv_load(int64_t NBR, const int32_t* __restrict__ vertex_of_r
     const double s0 = dscale[2 * row], s1 = dscale[2 * row + 1];
     o = make_double2(s0 > 0 ? xin[2 * rk] / s0 : 0.0, s1 > 0 ? xin[2 * rk + 1] / s1 : 0.0);
   }
-  r[row] = o;
-  p0[row] = make_double2(0.0, 0.0);
+  d4 rec;
+  rec.x = o.x;
+  rec.y = o.y;
+  rec.z = rec.w = 0.0;
+  rp[row] = rec;
 }
 __global__ void k_spmv_store(int64_t NBR, const int32_t* __restrict__ vertex_of_row,
                              const int32_t* __restrict__ vrank, int64_t v0, int64_t v1,
@@ -631,7 +635,7 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
   k_store_params<<<1, 32, 0, st>>>(make_ptrs(b, 1 << 30), dP);
   k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc, b.cta_first, b.cta_count, b.partB);
   k_compact_active<<<1, 1024, 0, st>>>(dP);
-  k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (double2*)b.r, (double2*)b.p0);
+  k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (d4*)b.rp);
   pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(dP, 0);
   k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, (const double2*)b.q, d_y);
   return cudaGetLastError();
