@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 EXPORTS = [
     "fea_version", "fea_ctx_create", "fea_ctx_create_prio", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
-    "fea_ctx_wait_ctx", "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
+    "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
     "fea_batch_download_images", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
     "fea_batch_get_timed_launches",
@@ -62,6 +62,8 @@ class SolveStats(C.Structure):
         ("spmv_launches_timed", C.c_int32), ("update_launches_timed", C.c_int32),
         ("spmv_ms_avg", C.c_float), ("update_ms_avg", C.c_float), ("solve_ms", C.c_float),
         ("kernel_launches", C.c_int64),
+        ("cluster_systems", C.c_int32), ("cluster_count", C.c_int32), ("cluster_iterations", C.c_int64),
+        ("cluster_ms", C.c_float), ("cluster_size", C.c_int32),
     ]
 
     def as_dict(self):
@@ -88,6 +90,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_ctx_create_prio": (C.c_int, [C.c_int, C.c_int, C.POINTER(P)]),
         "fea_ctx_destroy": (C.c_int, [P]),
         "fea_ctx_wait_ctx": (C.c_int, [P, P]),
+        "fea_ctx_set_int": (C.c_int, [P, C.c_char_p, C.c_int64]),
         "fea_last_error": (C.c_char_p, [P]),
         "fea_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
         "fea_host_free": (C.c_int, [P, P]),

@@ -108,6 +108,7 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   if (const char* v = getenv("FEA_NO_GRAPHS")) ctx->c.use_graphs = atoi(v) ? 0 : 1;
+  if (const char* v = getenv("FEA_PCG_PATH")) ctx->c.pcg_path = (strcmp(v, "stream") == 0 || atoi(v) == 1) ? 1 : 0;
   if (cudaHostAlloc((void**)&ctx->c.h_flag, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
       cudaMalloc(&ctx->c.d_pcg_params, kPcgParamBytes) != cudaSuccess) {
     if (ctx->c.h_flag) cudaFreeHost(ctx->c.h_flag);
@@ -120,6 +121,8 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   cudaEventCreateWithFlags(&ctx->c.ev_poll[1], cudaEventDisableTiming);
   cudaEventCreate(&ctx->c.ev_t0);
   cudaEventCreate(&ctx->c.ev_t1);
+  cudaEventCreate(&ctx->c.ev_c0);
+  cudaEventCreate(&ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   ctx->c.events.resize(3 * kMaxTimed);
@@ -138,6 +141,8 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaEventDestroy(ctx->c.ev_poll[1]);
   cudaEventDestroy(ctx->c.ev_t0);
   cudaEventDestroy(ctx->c.ev_t1);
+  cudaEventDestroy(ctx->c.ev_c0);
+  cudaEventDestroy(ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
   cudaEventDestroy(ctx->ev_join);
   cudaFreeHost(ctx->c.h_flag);
@@ -188,6 +193,14 @@ int fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other) {
   CK(ctx, cudaStreamWaitEvent(ctx->c.stream, other->ev_join, 0));
   return FEA_OK;
 }
+int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return FEA_BAD_ARG;
+  if (strcmp(key, "pcg_path") == 0) ctx->c.pcg_path = value == 1 ? 1 : 0;
+  else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;
+  else if (strcmp(key, "use_graphs") == 0) ctx->c.use_graphs = value ? 1 : 0;
+  else return fail(ctx, FEA_BAD_ARG, "unknown option key");
+  return FEA_OK;
+}
 int fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out) {
   if (!ctx || !out) return FEA_BAD_ARG;
   *out = ctx->c.launches;
@@ -229,6 +242,17 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
     b.NBR += pad;
     b.max_cta_count = std::max<int32_t>(b.max_cta_count, (int32_t)(pad / kCtaRows));  // upper bound
   }
+  // on-chip solver path: every system is assigned a cluster class by its own size alone
+  std::vector<int32_t> order;
+  for (int cls = 0; cls < 2; ++cls) {
+    b.cl_off[cls] = (int32_t)order.size();
+    for (int s = 0; s < ns; ++s)
+      if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s]) == cls) order.push_back(s);
+    b.cl_cnt[cls] = (int32_t)order.size() - b.cl_off[cls];
+    std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) {
+      return b.vtx_off[x + 1] - b.vtx_off[x] > b.vtx_off[y + 1] - b.vtx_off[y];
+    });
+  }
   cudaStream_t st = ctx->c.stream;
   int32_t* conn_local = nullptr;
   int8_t* creg_local = nullptr;
@@ -255,6 +279,9 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(dalloc(b, &b.cta_count, ns));
   A(dalloc(b, &b.err_flag, 4));
   A(dalloc(b, &b.empty, ns));
+  A(dalloc(b, &b.cl_order, ns));
+  A(dalloc(b, &b.cl_counter, 2));
+  if (!order.empty()) A(cudaMemcpyAsync(b.cl_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
   A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
   A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));
   A(cudaMemcpyAsync(b.xy, d->xy, sizeof(double) * b.NV * 2, cudaMemcpyHostToDevice, st));

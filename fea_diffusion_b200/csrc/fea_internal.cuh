@@ -33,7 +33,10 @@ struct Ctx {
   std::vector<cudaEvent_t> events;     // 3 per timed launch
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;  // around the cluster-path kernel
   int use_graphs = 1;                  // env FEA_NO_GRAPHS=1 disables
+  int pcg_path = 0;                    // 0 = auto (on-chip cluster kernel where systems fit), 1 = streaming only
+  int cluster_capacity[2] = {-1, -1};  // co-resident clusters of 4 / 8 CTAs (-1 = not queried yet)
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
   int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };
@@ -86,6 +89,9 @@ struct Batch {
   int32_t* cta_count = nullptr;      // [ns]
   int32_t max_cta_count = 0;         // host copy: most CTAs any one system owns
   int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
+  int32_t* cl_order = nullptr;       // [ns] systems of the cluster path: class 0 then class 1
+  int32_t cl_off[2] = {0, 0}, cl_cnt[2] = {0, 0};
+  int32_t* cl_counter = nullptr;     // [2] device work-queue heads
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending
@@ -138,6 +144,10 @@ cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d
 // whole lock-step PCG loop (init, chunks of kChunk iterations, polling); fills b.stats / timings
 cudaError_t run_pcg(Batch& b, double rtol, int max_iter);
 void pcg_release(Ctx& c);                                     // destroys the cached graphs
+int pcg_cluster_class(int64_t n_vertices_of_sample);          // 0: 4-CTA cluster, 1: 8-CTA, -1: streaming
+int pcg_cluster_capacity(Ctx& c, int cl);                     // co-resident clusters (0 = unavailable)
+struct PcgPtrs;
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl);
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);

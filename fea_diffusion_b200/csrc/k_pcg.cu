@@ -31,8 +31,13 @@
 #include <cstdlib>
 
 #include "fea_internal.cuh"
+#include "pcg_params.cuh"
 
 namespace fea {
+
+#ifdef FEA_CLUSTER_PROFILE
+void pcg_cluster_profile_dump();
+#endif
 
 constexpr int kT = kCtaRows;       // threads per CTA
 constexpr int kDirectSumMax = 128;  // partials a consumer warp sums itself
@@ -57,33 +62,6 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
   return warp_sum(acc);
 }
 
-// Everything the solver kernels need, resident in device memory (Ctx::d_pcg_params) instead of
-// being passed by value: the kernel nodes of an instantiated CUDA graph then carry no batch
-// pointers, so one graph per grid size serves every batch the context ever solves.
-struct PcgPtrs {
-  const int32_t* sys_of_cta;
-  const int32_t* cta_first;
-  const int32_t* cta_count;
-  const int32_t* slice_len;
-  const int64_t* slice_ptr;
-  const d4* val;
-  const int32_t* col;
-  const double* dcoup;
-  double2* x;
-  d4* rp;            // (r.x, r.y, p.x, p.y) per block row; p = direction of the PREVIOUS iteration
-  double2* q;
-  double* partA;
-  double* partB;
-  SysScalars sc;
-  double* rz_last;
-  int4* active;      // compacted work list: (cta, system, first cta of system, cta count)
-  int32_t n_active;  // valid entries of `active` (written by k_compact_active)
-  int32_t ncta;      // CTAs of the whole batch
-  int32_t ns;
-  int32_t max_iter;
-  int32_t two_level;
-};
-static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
 
 // U = entries whose loads are issued together before any of them is consumed (memory-level
 // parallelism per thread); MINB = minimum resident CTAs per SM asked of the register allocator.
@@ -340,6 +318,12 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   P.ns = b.ns;
   P.max_iter = max_iter;
   P.two_level = b.max_cta_count > kDirectSumMax ? 1 : 0;
+  P.cl_order = b.cl_order;
+  for (int k = 0; k < 2; ++k) {
+    P.cl_off[k] = b.cl_off[k];
+    P.cl_cnt[k] = b.cl_cnt[k];
+  }
+  P.cl_counter = b.cl_counter;
   return P;
 }
 
@@ -393,7 +377,12 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   cudaStream_t st = c.stream;
   const int ncta = (int)(b.NBR / kCtaRows);
   PcgPtrs* dP = (PcgPtrs*)c.d_pcg_params;
-  const PcgPtrs P = make_ptrs(b, max_iter);
+  PcgPtrs P = make_ptrs(b, max_iter);
+  int n_cluster = 0;
+  for (int k = 0; k < 2; ++k) {
+    if (c.pcg_path != 0 || pcg_cluster_capacity(c, k ? 8 : 4) <= 0) P.cl_cnt[k] = 0;
+    n_cluster += P.cl_cnt[k];
+  }
   const bool two = P.two_level != 0;
   const int per_iter = two ? 4 : 2;
   int64_t launches = 0;
@@ -406,12 +395,23 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   cudaMemsetAsync(b.sc.n_done, 0, sizeof(int32_t), st);
   if (ncta) k_pcg_init_vectors<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
+  launches += 3;
+  if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
+    cudaMemsetAsync(b.cl_counter, 0, 2 * sizeof(int32_t), st);
+    cudaEventRecord(c.ev_c0, st);
+    for (int k = 1; k >= 0; --k) {   // the few large systems (8-CTA clusters) first
+      if (!P.cl_cnt[k]) continue;
+      if ((e = launch_pcg_cluster(c, dP, P.cl_cnt[k], k ? 8 : 4)) != cudaSuccess) return e;
+      launches += 1;
+    }
+    cudaEventRecord(c.ev_c1, st);
+  }
   k_compact_active<<<1, 1024, 0, st>>>(dP);
-  launches += 4;
+  launches += 1;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   std::vector<int> done_after;  // finished systems observed after chunk k
   int timed = 0, k = 0;
-  if (ncta) {
+  if (ncta && n_cluster < b.ns) {
     const int max_chunks = (max_iter + kChunk - 1) / kChunk + 2;
     int n_active = ncta;  // stale upper bound of the work-list length
     for (; k < max_chunks; ++k) {
@@ -463,6 +463,25 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   }
   b.stats.iterations = itmax;
   b.stats.n_converged = nconv;
+  if (n_cluster > 0) {
+    std::vector<int32_t> order(b.cl_off[1] + b.cl_cnt[1]);
+    if ((e = cudaMemcpy(order.data(), b.cl_order, sizeof(int32_t) * order.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    int64_t tot = 0;
+    int nclusters = 0;
+    for (int k = 0; k < 2; ++k) {
+      for (int i = 0; i < P.cl_cnt[k]; ++i) tot += it[order[b.cl_off[k] + i]];
+      const int capn = pcg_cluster_capacity(c, k ? 8 : 4);
+      if (P.cl_cnt[k]) nclusters += P.cl_cnt[k] < capn ? P.cl_cnt[k] : capn;
+    }
+    b.stats.cluster_systems = n_cluster;
+    b.stats.cluster_size = P.cl_cnt[0] >= P.cl_cnt[1] ? 4 : 8;   // the class that solved most systems
+    b.stats.cluster_count = nclusters;
+    b.stats.cluster_iterations = tot;
+    cudaEventElapsedTime(&b.stats.cluster_ms, c.ev_c0, c.ev_c1);
+#ifdef FEA_CLUSTER_PROFILE
+    pcg_cluster_profile_dump();
+#endif
+  }
   b.t_spmv.assign(timed, 0.f);
   b.t_update.assign(timed, 0.f);
   for (int t = 0; t < timed; ++t) {

@@ -1,0 +1,397 @@
+// K5 (on-chip path): Jacobi-PCG of one system per thread-block cluster, matrix resident in shared
+// memory -- replaces Newton + ScipyDirect(SuperLU) + SimpleTimeSteppingSolver (reference
+// datagen/fea_analysis.py:371-375, 425-439) for the plate-sized systems of the data-synthesis loop.
+//
+// A default-density plate has 2.5-10 k vertices: its scaled block-SELL matrix is 0.5-2.3 MB and its
+// CG vectors a few hundred KB.  That fits the shared memory + registers of 8 SMs, so a cluster of
+// 8 CTAs x 512 threads keeps ONE system on chip for its whole solve:
+//
+//   * every CTA owns a contiguous range of the system's 32-row slices; its slices of the matrix
+//     are copied from HBM to shared memory ONCE (slices that do not fit stay in global memory and
+//     are streamed from L2 every iteration);
+//   * x, r, p of a thread's (up to 4) block rows live in registers for the whole solve;
+//   * the search direction p is published in shared memory and gathered by the neighbours
+//     through distributed shared memory (ld.shared::cluster); the gather addresses are
+//     precomputed when the matrix is loaded;
+//   * dot products: every warp pushes its partial into a table in all 8 CTAs (st.shared::cluster);
+//     after the barrier every warp adds its local copy in the same fixed order -- no atomics,
+//     bitwise reproducible, independent of which cluster or SM runs the system;
+//   * three cluster barriers per iteration (p published, p.q partials, r.r partials).
+//
+// Clusters are persistent and pull systems from a queue (largest first), so there is no lock-step
+// and no tail of idle CTAs waiting for the slowest system of a batch.  HBM traffic is one read of
+// the matrix and vectors per SOLVE instead of per iteration.
+// Systems too large for a cluster (> 16 384 block rows) keep using the streaming kernels of k_pcg.cu.
+#include <cooperative_groups.h>
+
+#include <cstdio>
+
+#include "fea_internal.cuh"
+#include "pcg_params.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fea {
+
+#ifdef FEA_CLUSTER_PROFILE
+__device__ unsigned long long g_cl_prof[16];
+#define PROF_T(i) do { if (prof) { const long long t_ = clock64(); pt[i] += t_ - t0_; t0_ = t_; } } while (0)
+#else
+#define PROF_T(i) do { } while (0)
+#endif
+
+constexpr int kClMax = 8;                   // largest cluster (portable maximum)
+#ifndef FEA_CL_THREADS
+#define FEA_CL_THREADS 512
+#endif
+constexpr int kClT = FEA_CL_THREADS;        // threads per CTA
+constexpr int kClW = kClT / 32;             // warps per CTA
+constexpr int kClRpt = 2048 / kClT;         // block rows per thread (2048 rows per CTA at most)
+constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64)
+constexpr int kClSmemBytes = 227 * 1024;    // dynamic shared memory per CTA
+
+struct ClHeader {                 // start of the dynamic shared memory of every CTA
+  double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
+  double partB[kClMax * kClW];    // r.r partials (each warp pushes its partial to all CTAs)
+  int32_t next_sys;               // (rank 0) queue entry the cluster works on next
+  int32_t pad_;
+  int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
+  int32_t s_len[kClSlices];       // blocks per row of the slice
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double2 ld_cluster_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared::cluster.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 ld_shared_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+// gather of a published p entry: bit 0 of the precomputed address marks an entry of ANOTHER CTA
+// (distributed shared memory, ~20 B/clk per SM); own entries use the plain 128 B/clk path
+__device__ __forceinline__ double2 ld_p(uint32_t g) {
+  return (g & 1u) ? ld_cluster_f64x2(g & ~1u) : ld_shared_f64x2(g);
+}
+__device__ __forceinline__ double ld_cluster_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int ld_cluster_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// Dot products over the cluster, push model: lane c < 8 of every warp stores the warp's partial
+// into slot [rank][warp] of CTA c's table; after the cluster barrier every warp of every CTA adds
+// the 128 slots of its own copy in the same fixed order, so all of them hold the same bits and no
+// intra-CTA broadcast is needed.
+template <int CL>
+__device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, int rank, int warp, int lane, double v) {
+  if (lane < CL) st_cluster_f64(mapa_u32(smem_u32(h) + field_off + 8u * (uint32_t)(rank * kClW + warp), lane), v);
+}
+template <int CL>
+__device__ __forceinline__ double sum_table(const double* t, int lane) {
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < CL * kClW / 32; ++i) acc += t[lane + 32 * i];
+  return warp_sum(acc);
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
+  constexpr int kCl = CL;
+  constexpr int kClass = CL == 4 ? 0 : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const PcgPtrs& P = *Pp;
+  ClHeader* h = reinterpret_cast<ClHeader*>(smem);
+  constexpr int kHdr = (sizeof(ClHeader) + 127) / 128 * 128;
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+  for (;;) {
+    // ---- next system of the queue (rank 0 pulls, everyone reads it through DSMEM) --------------
+    if (rank == 0 && tid == 0) h->next_sys = atomicAdd(P.cl_counter + kClass, 1);
+    cluster.sync();
+    const int qi = ld_cluster_s32(mapa_u32(smem_u32(&h->next_sys), 0));
+    if (qi >= P.cl_cnt[kClass]) {   // uniform over the cluster
+      cluster.sync();          // rank 0's shared memory must outlive everybody's read of next_sys
+      break;
+    }
+    const int s = P.cl_order[P.cl_off[kClass] + qi];
+    if (P.sc.done[s]) { cluster.sync(); continue; }   // empty / zero-load systems (init_scalars)
+
+    // ---- geometry of the system inside the cluster ----------------------------------------------
+    const int64_t row0 = (int64_t)P.cta_first[s] * kCtaRows;       // first block row of the system
+    const int n_sl = P.cta_count[s] * (kCtaRows / 32);             // 32-row slices of the system
+    const int Sc = (n_sl + kCl - 1) / kCl;                         // slices per CTA (<= kClSlices)
+    const int Rc = Sc * 32;                                        // rows per CTA
+    const int my_sl = max(0, min(Sc, n_sl - rank * Sc));           // slices this CTA owns
+    const int64_t my_row0 = row0 + (int64_t)rank * Rc;
+    double2* pbuf = reinterpret_cast<double2*>(smem + kHdr);       // [Rc] published p
+    double* dcs = reinterpret_cast<double*>(smem + kHdr + Rc * 16); // [Rc] diagonal-block couplings
+    const int mat0 = kHdr + ((Rc * 24 + 127) / 128) * 128;         // matrix area
+    const int cap = kClSmemBytes - mat0;
+
+    // ---- slice table + copy of the CTA's matrix slices into shared memory ------------------------
+    if (tid < kClSlices) {
+      h->s_len[tid] = tid < my_sl ? P.slice_len[(my_row0 >> 5) + tid] : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int off = 0;
+      for (int i = 0; i < kClSlices; ++i) {
+        const int bytes = h->s_len[i] * 32 * 36;   // 32-byte block + 4-byte gather address per entry
+        if (i < my_sl && off + bytes <= cap) { h->s_off[i] = off; off += bytes; }
+        else h->s_off[i] = -1;
+      }
+    }
+    __syncthreads();
+    const uint32_t pbuf_a = smem_u32(pbuf);
+#pragma unroll
+    for (int k = 0; k < kClRpt; ++k) {
+      const int ls = warp + kClW * k;        // local slice handled by this warp
+      if (ls >= my_sl) continue;
+      const int off = h->s_off[ls];
+      if (off < 0) continue;
+      const int L = h->s_len[ls];
+      const int64_t base = P.slice_ptr[(my_row0 >> 5) + ls];
+      // per slice: L x 32 top halves (k00,k01), L x 32 bottom halves (k10,k11), L x 32 addresses
+      // (16-byte lane stride: conflict-free 128-bit shared loads)
+      double2* st = reinterpret_cast<double2*>(smem + mat0 + off);
+      double2* sb = st + L * 32;
+      uint32_t* sa = reinterpret_cast<uint32_t*>(sb + L * 32);
+      for (int j = 0; j < L; ++j) {
+        const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
+        st[j * 32 + lane] = make_double2(blk.x, blk.y);
+        sb[j * 32 + lane] = make_double2(blk.z, blk.w);
+        const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;   // row inside the system
+        const int cr = c / Rc;
+        const uint32_t la = pbuf_a + 16u * (uint32_t)(c - cr * Rc);
+        sa[j * 32 + lane] = cr == rank ? la : (mapa_u32(la, (uint32_t)cr) | 1u);
+      }
+    }
+
+    // ---- vectors of the thread's rows in registers ----------------------------------------------
+    double2 x[kClRpt], r[kClRpt];   // p lives in pbuf (its owner is the only writer)
+    bool own[kClRpt];
+#pragma unroll
+    for (int k = 0; k < kClRpt; ++k) {
+      const int lr = tid + kClT * k;
+      own[k] = lr < my_sl * 32;
+      x[k] = make_double2(0.0, 0.0);
+      r[k] = x[k];
+      if (own[k]) {
+        pbuf[lr] = x[k];
+        const d4 rec = P.rp[my_row0 + lr];   // r0 = S b (k_pcg_init_vectors)
+        r[k] = make_double2(rec.x, rec.y);
+        dcs[lr] = P.dcoup[my_row0 + lr];
+      }
+    }
+#ifdef FEA_CLUSTER_PROFILE
+    const bool prof = rank == 0 && tid == 0;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0_ = clock64();
+#endif
+    double rz = P.sc.rz[0][s], rz_prev = inf;
+    const double tol2 = P.sc.tol2[s];
+    const int max_iter = P.max_iter;
+    int iters = 0, status = FEA_SAMPLE_NOT_RUN;
+
+    for (;;) {
+      if (!isfinite(rz)) status = FEA_SAMPLE_BREAKDOWN;
+      else if (rz <= tol2) status = FEA_SAMPLE_CONVERGED;
+      else if (iters >= max_iter) status = FEA_SAMPLE_MAX_ITER;
+      if (status != FEA_SAMPLE_NOT_RUN) break;
+      const double beta = rz / rz_prev;
+#pragma unroll
+      for (int k = 0; k < kClRpt; ++k) {
+        if (own[k]) {
+          double2 pv = pbuf[tid + kClT * k];
+          pv.x = fma(beta, pv.x, r[k].x);
+          pv.y = fma(beta, pv.y, r[k].y);
+          pbuf[tid + kClT * k] = pv;
+        }
+      }
+      PROF_T(0);
+      cluster.sync();                                           // S1: every CTA's p is visible
+      PROF_T(1);
+      double2 q[kClRpt];
+      double part = 0.0;
+#pragma unroll
+      for (int k = 0; k < kClRpt; ++k) {
+        const int ls = warp + kClW * k;
+        double a0 = 0.0, a1 = 0.0;
+        double2 pk = make_double2(0.0, 0.0);
+        if (ls < my_sl) {
+          pk = pbuf[tid + kClT * k];
+          const double dck = dcs[tid + kClT * k];
+          a0 = fma(dck, pk.y, pk.x);
+          a1 = fma(dck, pk.x, pk.y);
+          const int L = h->s_len[ls];
+          const int off = h->s_off[ls];
+          if (off >= 0) {
+            const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
+            const double2* sb = st + L * 32;
+            const uint32_t* sa = reinterpret_cast<const uint32_t*>(sb + L * 32 - lane) + lane;
+            const uint32_t self = pbuf_a + 16u * (uint32_t)(tid + kClT * k);
+            for (int j = 0; j < L; j += 4) {   // 4 gathers in flight; the tail round is predicated
+              uint32_t g[4];
+              double2 pj[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u]) : make_double2(0.0, 0.0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (j + u < L) {
+                  const double2 kt = st[(j + u) * 32], kb = sb[(j + u) * 32];
+                  a0 = fma(kt.x, pj[u].x, a0); a0 = fma(kt.y, pj[u].y, a0);
+                  a1 = fma(kb.x, pj[u].x, a1); a1 = fma(kb.y, pj[u].y, a1);
+                }
+              }
+            }
+          } else {  // slice that did not fit: stream it from global memory (L2 resident)
+            const int64_t base = P.slice_ptr[(my_row0 >> 5) + ls] + lane;
+            for (int j = 0; j < L; ++j) {
+              const d4 k0 = ld_stream_d4(P.val + base + j * 32);
+              const int c = ld_stream_i32(P.col + base + j * 32) - (int)row0;
+              const int cr = c / Rc;
+              const double2 p0 = ld_cluster_f64x2(mapa_u32(pbuf_a + 16u * (uint32_t)(c - cr * Rc), (uint32_t)cr));
+              a0 = fma(k0.x, p0.x, a0); a0 = fma(k0.y, p0.y, a0);
+              a1 = fma(k0.z, p0.x, a1); a1 = fma(k0.w, p0.y, a1);
+            }
+          }
+        }
+        q[k] = make_double2(a0, a1);
+        part += own[k] ? fma(pk.x, a0, pk.y * a1) : 0.0;
+      }
+      part = warp_sum(part);
+      push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partA), rank, warp, lane, part);
+      PROF_T(2);
+      cluster.sync();                                           // S2: p.q partials visible
+      PROF_T(3);
+      const double pq = sum_table<CL>(h->partA, lane);
+      PROF_T(4);
+      if (!(pq > 0.0 && isfinite(pq))) { status = FEA_SAMPLE_BREAKDOWN; break; }
+      const double alpha = rz / pq;
+      part = 0.0;
+#pragma unroll
+      for (int k = 0; k < kClRpt; ++k) {
+        const double2 pk = own[k] ? pbuf[tid + kClT * k] : make_double2(0.0, 0.0);
+        x[k].x = fma(alpha, pk.x, x[k].x);
+        x[k].y = fma(alpha, pk.y, x[k].y);
+        r[k].x = fma(-alpha, q[k].x, r[k].x);
+        r[k].y = fma(-alpha, q[k].y, r[k].y);
+        part += own[k] ? fma(r[k].x, r[k].x, r[k].y * r[k].y) : 0.0;
+      }
+      part = warp_sum(part);
+      push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), rank, warp, lane, part);
+      PROF_T(5);
+      cluster.sync();                                           // S3: r.r partials visible
+      PROF_T(6);
+      rz_prev = rz;
+      rz = sum_table<CL>(h->partB, lane);
+      PROF_T(7);
+      ++iters;
+    }
+
+    // ---- results ------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kClRpt; ++k)
+      if (own[k]) P.x[my_row0 + tid + kClT * k] = x[k];
+#ifdef FEA_CLUSTER_PROFILE
+    if (prof) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_cl_prof[i], (unsigned long long)pt[i]);
+      atomicAdd(&g_cl_prof[8], (unsigned long long)iters);
+    }
+#endif
+    if (rank == 0 && tid == 0) {
+      P.sc.iters[s] = iters;
+      P.sc.status[s] = status;
+      P.sc.done[s] = 1;
+      P.rz_last[s] = rz;
+      atomicAdd(P.sc.n_done, 1);
+    }
+    cluster.sync();   // nobody may still be reading this CTA's shared memory when it is reused
+  }
+}
+
+typedef void (*cluster_fn)(const PcgPtrs*);
+static cluster_fn cluster_kernel(int cl) {
+  switch (cl) {
+    case 4: return k_pcg_cluster<4>;
+    default: return k_pcg_cluster<8>;
+  }
+}
+
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int cl, int nclusters, cudaStream_t st) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(cl * nclusters);
+  cfg->blockDim = dim3(kClT);
+  cfg->dynamicSmemBytes = kClSmemBytes;
+  cfg->stream = st;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg->attrs = at;
+  cfg->numAttrs = 1;
+}
+
+// Co-resident clusters of `cl` CTAs (0 = path unavailable on this device).
+int pcg_cluster_capacity(Ctx& c, int cl) {
+  const int slot = cl == 4 ? 0 : 1;
+  if (c.cluster_capacity[slot] >= 0) return c.cluster_capacity[slot];
+  c.cluster_capacity[slot] = 0;
+  if (cudaFuncSetAttribute(cluster_kernel(cl), cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  cluster_config(&cfg, at, cl, 256, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, cluster_kernel(cl), &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  c.cluster_capacity[slot] = n;
+  return n;
+}
+
+// Cluster class of a system from its vertex count (an upper bound of its block rows): 0 = 4 CTAs
+// (up to 8192 rows), 1 = 8 CTAs (up to 16384 rows), -1 = too large, streaming kernels.
+int pcg_cluster_class(int64_t n_vertices_of_sample) {
+  const int64_t pad = (n_vertices_of_sample + kCtaRows - 1) / kCtaRows * kCtaRows;
+  if (pad <= 0) return -1;
+  if (pad / 32 <= 4 * (int64_t)kClSlices) return 0;
+  if (pad / 32 <= 8 * (int64_t)kClSlices) return 1;
+  return -1;
+}
+
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl) {
+  const int capn = pcg_cluster_capacity(c, cl);
+  if (capn <= 0 || n_systems <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  cluster_config(&cfg, at, cl, n_systems < capn ? n_systems : capn, c.stream);
+  return cudaLaunchKernelEx(&cfg, cluster_kernel(cl), dP);
+}
+
+}  // namespace fea

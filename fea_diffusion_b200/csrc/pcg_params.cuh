@@ -1,0 +1,42 @@
+// Device-resident parameter block shared by the PCG kernels (k_pcg.cu, k_pcg_cluster.cu).
+#pragma once
+#include "fea_internal.cuh"
+
+namespace fea {
+
+// Everything the solver kernels need, resident in device memory (Ctx::d_pcg_params) instead of
+// being passed by value: the kernel nodes of an instantiated CUDA graph then carry no batch
+// pointers, so one graph per grid size serves every batch the context ever solves.
+struct PcgPtrs {
+  const int32_t* sys_of_cta;
+  const int32_t* cta_first;
+  const int32_t* cta_count;
+  const int32_t* slice_len;
+  const int64_t* slice_ptr;
+  const d4* val;
+  const int32_t* col;
+  const double* dcoup;
+  double2* x;
+  d4* rp;            // (r.x, r.y, p.x, p.y) per block row; p = direction of the PREVIOUS iteration
+  double2* q;
+  double* partA;
+  double* partB;
+  SysScalars sc;
+  double* rz_last;
+  int4* active;      // compacted work list: (cta, system, first cta of system, cta count)
+  int32_t n_active;  // valid entries of `active` (written by k_compact_active)
+  int32_t ncta;      // CTAs of the whole batch
+  int32_t ns;
+  int32_t max_iter;
+  int32_t two_level;
+  // cluster path (k_pcg_cluster.cu): systems small enough to stay on chip.  The cluster size is
+  // a function of the system alone (class 0: 4 CTAs, class 1: 8 CTAs), so that its summation
+  // order -- and therefore every bit of its result -- does not depend on the rest of the batch.
+  const int32_t* cl_order;  // eligible systems: class 0 first, then class 1; largest first in each
+  int32_t cl_off[2];        // first entry of each class in cl_order
+  int32_t cl_cnt[2];        // entries of each class (0 = class not launched)
+  int32_t* cl_counter;      // [2] work-queue heads (device counters, zeroed per solve)
+};
+static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
+
+}  // namespace fea

@@ -140,6 +140,10 @@ class Context:
         """Stream-order this context after everything submitted to ``other`` so far."""
         self._check(self.lib.fea_ctx_wait_ctx(self.h, other.h))
 
+    def set_option(self, key: str, value: int):
+        """fea_ctx_set_int: "pcg_path" (0 auto / 1 streaming kernels only), "spmv_variant", "use_graphs"."""
+        self._check(self.lib.fea_ctx_set_int(self.h, key.encode("ascii"), int(value)))
+
     def kernel_launches(self) -> int:
         n = C.c_int64()
         self._check(self.lib.fea_ctx_kernel_launches(self.h, C.byref(n)))

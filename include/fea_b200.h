@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define FEA_VERSION_MAJOR 0
-#define FEA_VERSION_MINOR 1
+#define FEA_VERSION_MINOR 2
 
 typedef struct fea_ctx fea_ctx;
 typedef struct fea_batch fea_batch;
@@ -100,6 +100,12 @@ typedef struct fea_solve_stats {
   float   update_ms_avg;    /* same for the fused vector-update kernel */
   float   solve_ms;         /* whole PCG loop, CUDA events on the ctx stream */
   int64_t kernel_launches;  /* kernels launched by this solve */
+  /* on-chip path (one system per thread-block cluster, matrix in shared memory) */
+  int32_t cluster_systems;     /* systems solved by k_pcg_cluster in this solve */
+  int32_t cluster_count;       /* clusters launched */
+  int64_t cluster_iterations;  /* sum of their iteration counts */
+  float   cluster_ms;          /* CUDA-event duration of that kernel */
+  int32_t cluster_size;        /* CTAs per cluster (4 or 8) of the class that solved most systems */
 } fea_solve_stats;
 
 /* ---- library / context -------------------------------------------------- */
@@ -121,6 +127,9 @@ int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_sto
 /* work submitted to ctx after this call starts only once everything submitted to `other` so far
  * has finished (same device): joins several contexts' streams for one event-timed region */
 int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
+/* integer options: "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
+ * the streaming kernels; "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
+int  fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this context has launched so far (graph nodes included) */
 int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
 

@@ -18,9 +18,13 @@ RTOL_SOLVER = 1e-11          # PCG stopping tolerance used by the tests
 TOL_U = 1e-8                 # north_star: rel-L2 displacement error vs the direct solve
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["onchip", "stream"])
+def ctx(request):
+    """Both solver paths: systems that fit a thread-block cluster stay on chip (k_pcg_cluster);
+    "stream" forces the lock-step streaming kernels (what ~1M-DOF systems always use)."""
     c = Context(0)
+    c.set_option("pcg_path", 1 if request.param == "stream" else 0)
+    c.path = request.param
     yield c
     c.close()
 
@@ -172,6 +176,24 @@ def test_raster(built, name, image_size):
         assert (r.images[0, c] != 255).sum() > 0.05 * size * size * min(1.0, (bbox[3] - bbox[1]) / (bbox[2] - bbox[0]))
 
 
+def test_both_solver_paths_agree(built, ctx):
+    """On-chip and streaming PCG differ only in summation order: same iterates to rounding."""
+    other = Context(0)
+    other.set_option("pcg_path", 0 if ctx.path == "stream" else 1)
+    try:
+        for name in ("cantilever", "gusset"):
+            setup, orc, b = built[name]
+            r1 = b.solve(RTOL_SOLVER, 40000).download()
+            with other.create_batch(pack([setup.sample])) as b2:
+                r2 = b2.assemble().solve(RTOL_SOLVER, 40000).download()
+                st2 = b2.stats()
+            st1 = b.stats()
+            assert rel(r1.u, r2.u) <= 1e-9 and abs(int(r1.iters[0]) - int(r2.iters[0])) <= 3
+            assert (st1["cluster_systems"], st2["cluster_systems"]) == ((1, 0) if ctx.path == "onchip" else (0, 1))
+    finally:
+        other.close()
+
+
 def test_singular_samples_are_reported(ctx):
     """(i) the reference's committed composite condition floats (F4): CG must not claim
     convergence; (ii) an active vertex with no stiffness cell is the reference's NaN path."""
@@ -236,4 +258,5 @@ def test_one_call_host_path(ctx, built):
     r = ctx.solve_batch(pack([setup.sample]), RTOL_SOLVER, 20000, image_size=size, affine=aff, value_scale=0.1)
     assert np.array_equal(r.u, staged.u) and np.array_equal(r.ranges, staged.ranges)
     assert r.images.shape == (1, 2, size, size) and (r.images != 255).any()
-    assert r.stats["kernel_launches"] > 0 and r.stats["spmv_ms_avg"] > 0
+    assert r.stats["kernel_launches"] > 0
+    assert (r.stats["cluster_ms"] > 0 and r.stats["cluster_systems"] == 1) if ctx.path == "onchip" else r.stats["spmv_ms_avg"] > 0
