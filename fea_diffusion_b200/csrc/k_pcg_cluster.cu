@@ -35,7 +35,7 @@ namespace fea {
 
 #ifdef FEA_CLUSTER_PROFILE
 __device__ unsigned long long g_cl_prof[16];
-#define PROF_T(i) do { if (prof) { const long long t_ = clock64(); pt[i] += t_ - t0_; t0_ = t_; } } while (0)
+#define PROF_T(i) do { if (prof) { const long long t_ = clock64(); h->prof[i] += t_ - h->prof[9]; h->prof[9] = t_; } } while (0)
 #else
 #define PROF_T(i) do { } while (0)
 #endif
@@ -57,6 +57,11 @@ struct ClHeader {                 // start of the dynamic shared memory of every
   int32_t pad_;
   int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
   int32_t s_len[kClSlices];       // blocks per row of the slice
+  int32_t s_aoff[kClSlices];      // entry offset of the slice's gather addresses
+  int64_t s_base[kClSlices];      // first entry of the slice in the global block-SELL arrays
+#ifdef FEA_CLUSTER_PROFILE
+  long long prof[10];
+#endif
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,37 +154,44 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
     const int cap = kClSmemBytes - mat0;
 
     // ---- slice table + copy of the CTA's matrix slices into shared memory ------------------------
+    // gather addresses (4 B per block) of ALL owned slices are kept on chip; the 32-byte blocks of
+    // as many slices as fit follow them, the rest is streamed from global memory (L2) every iteration
     if (tid < kClSlices) {
       h->s_len[tid] = tid < my_sl ? P.slice_len[(my_row0 >> 5) + tid] : 0;
+      h->s_base[tid] = tid < my_sl ? P.slice_ptr[(my_row0 >> 5) + tid] : 0;
     }
     __syncthreads();
     if (tid == 0) {
-      int off = 0;
+      int ent = 0;
+      for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += h->s_len[i] * 32; }
+      int off = (ent * 4 + 127) / 128 * 128;
       for (int i = 0; i < kClSlices; ++i) {
-        const int bytes = h->s_len[i] * 32 * 36;   // 32-byte block + 4-byte gather address per entry
+        const int bytes = h->s_len[i] * 32 * 32;
         if (i < my_sl && off + bytes <= cap) { h->s_off[i] = off; off += bytes; }
         else h->s_off[i] = -1;
       }
     }
     __syncthreads();
     const uint32_t pbuf_a = smem_u32(pbuf);
+    uint32_t* sa_all = reinterpret_cast<uint32_t*>(smem + mat0);
 #pragma unroll
     for (int k = 0; k < kClRpt; ++k) {
       const int ls = warp + kClW * k;        // local slice handled by this warp
       if (ls >= my_sl) continue;
       const int off = h->s_off[ls];
-      if (off < 0) continue;
       const int L = h->s_len[ls];
-      const int64_t base = P.slice_ptr[(my_row0 >> 5) + ls];
-      // per slice: L x 32 top halves (k00,k01), L x 32 bottom halves (k10,k11), L x 32 addresses
+      const int64_t base = h->s_base[ls];
+      uint32_t* sa = sa_all + h->s_aoff[ls];
+      // values per slice: L x 32 top halves (k00,k01) then L x 32 bottom halves (k10,k11)
       // (16-byte lane stride: conflict-free 128-bit shared loads)
-      double2* st = reinterpret_cast<double2*>(smem + mat0 + off);
+      double2* st = reinterpret_cast<double2*>(smem + mat0 + (off < 0 ? 0 : off));
       double2* sb = st + L * 32;
-      uint32_t* sa = reinterpret_cast<uint32_t*>(sb + L * 32);
       for (int j = 0; j < L; ++j) {
-        const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
-        st[j * 32 + lane] = make_double2(blk.x, blk.y);
-        sb[j * 32 + lane] = make_double2(blk.z, blk.w);
+        if (off >= 0) {
+          const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
+          st[j * 32 + lane] = make_double2(blk.x, blk.y);
+          sb[j * 32 + lane] = make_double2(blk.z, blk.w);
+        }
         const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;   // row inside the system
         const int cr = c / Rc;
         const uint32_t la = pbuf_a + 16u * (uint32_t)(c - cr * Rc);
@@ -205,8 +217,10 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
     }
 #ifdef FEA_CLUSTER_PROFILE
     const bool prof = rank == 0 && tid == 0;
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t0_ = clock64();
+    if (prof) {
+      for (int i = 0; i < 9; ++i) h->prof[i] = 0;
+      h->prof[9] = clock64();
+    }
 #endif
     double rz = P.sc.rz[0][s], rz_prev = inf;
     const double tol2 = P.sc.tol2[s];
@@ -245,11 +259,11 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
           a1 = fma(dck, pk.x, pk.y);
           const int L = h->s_len[ls];
           const int off = h->s_off[ls];
+          const uint32_t* sa = sa_all + h->s_aoff[ls] + lane;
+          const uint32_t self = pbuf_a + 16u * (uint32_t)(tid + kClT * k);
           if (off >= 0) {
             const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
             const double2* sb = st + L * 32;
-            const uint32_t* sa = reinterpret_cast<const uint32_t*>(sb + L * 32 - lane) + lane;
-            const uint32_t self = pbuf_a + 16u * (uint32_t)(tid + kClT * k);
             for (int j = 0; j < L; j += 4) {   // 4 gathers in flight; the tail round is predicated
               uint32_t g[4];
               double2 pj[4];
@@ -266,15 +280,26 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
                 }
               }
             }
-          } else {  // slice that did not fit: stream it from global memory (L2 resident)
-            const int64_t base = P.slice_ptr[(my_row0 >> 5) + ls] + lane;
-            for (int j = 0; j < L; ++j) {
-              const d4 k0 = ld_stream_d4(P.val + base + j * 32);
-              const int c = ld_stream_i32(P.col + base + j * 32) - (int)row0;
-              const int cr = c / Rc;
-              const double2 p0 = ld_cluster_f64x2(mapa_u32(pbuf_a + 16u * (uint32_t)(c - cr * Rc), (uint32_t)cr));
-              a0 = fma(k0.x, p0.x, a0); a0 = fma(k0.y, p0.y, a0);
-              a1 = fma(k0.z, p0.x, a1); a1 = fma(k0.w, p0.y, a1);
+          } else {  // blocks that did not fit: streamed from global memory (L2 resident), 4 in flight
+            const d4* vt = P.val + h->s_base[ls] + lane;
+            for (int j = 0; j < L; j += 4) {
+              uint32_t g[4];
+              d4 kv[4];
+              double2 pj[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                kv[u].x = kv[u].y = kv[u].z = kv[u].w = 0.0;
+                if (j + u < L) kv[u] = ld_stream_d4(vt + (j + u) * 32);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u]) : make_double2(0.0, 0.0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
+                a1 = fma(kv[u].z, pj[u].x, a1); a1 = fma(kv[u].w, pj[u].y, a1);
+              }
             }
           }
         }
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
       if (own[k]) P.x[my_row0 + tid + kClT * k] = x[k];
 #ifdef FEA_CLUSTER_PROFILE
     if (prof) {
-      for (int i = 0; i < 8; ++i) atomicAdd(&g_cl_prof[i], (unsigned long long)pt[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_cl_prof[i], (unsigned long long)h->prof[i]);
       atomicAdd(&g_cl_prof[8], (unsigned long long)iters);
     }
 #endif
@@ -374,6 +399,18 @@ int pcg_cluster_capacity(Ctx& c, int cl) {
   c.cluster_capacity[slot] = n;
   return n;
 }
+
+#ifdef FEA_CLUSTER_PROFILE
+void pcg_cluster_profile_dump() {
+  unsigned long long h[16];
+  cudaMemcpyFromSymbol(h, g_cl_prof, sizeof(h));
+  const char* names[8] = {"p publish", "S1 barrier", "spmv + warp partial", "S2 barrier", "sum A", "update", "S3 barrier", "sum B"};
+  const double it = (double)(h[8] ? h[8] : 1);
+  for (int i = 0; i < 8; ++i) fprintf(stderr, "[cluster prof] %-20s %8.0f cycles/iter\n", names[i], h[i] / it);
+  unsigned long long z[16] = {};
+  cudaMemcpyToSymbol(g_cl_prof, z, sizeof(z));
+}
+#endif
 
 // Cluster class of a system from its vertex count (an upper bound of its block rows): 0 = 4 CTAs
 // (up to 8192 rows), 1 = 8 CTAs (up to 16384 rows), -1 = too large, streaming kernels.
