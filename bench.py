@@ -124,7 +124,7 @@ def oracle_unit(job):
     p.ranges_lines(u)
     for c in range(2):
         ro.rasterize_scalar(p.coors, p.conn, u[1][:, c], size, affine)
-    return float(np.abs(u[-1]).max())
+    return u[-1]
 
 
 def jobs_of(items, num_steps):
@@ -342,9 +342,13 @@ def run_b200(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         jobs = jobs_of(items[:a.cpu_samples], a.steps_per_condition)
         t0 = time.perf_counter()
-        for j in jobs:
-            oracle_unit(j)
+        u_cpu = [oracle_unit(j) for j in jobs]
         dt = time.perf_counter() - t0
+        # the same samples from the timed GPU step against the CPU direct solve (north_star: <= 1e-8)
+        u_gpu = packed.split_vertices(res0.u)
+        errs = [float(np.linalg.norm(u_gpu[i] - u_cpu[i]) / np.linalg.norm(u_cpu[i])) for i in range(len(jobs))]
+        line["parity"] = {"samples": len(jobs), "max_rel_l2_vs_cpu_direct_solve": max(errs), "tolerance": 1e-8,
+                          "ok": bool(max(errs) <= 1e-8)}
         line["cpu_baseline"] = {"value": len(jobs) / dt, "unit": "solves/s", "cores": 1, "kind": "port",
                                 "host_cores_available": os.cpu_count(),
                                 "sample": "first %d plate-conditions of the workload, %.1f s, reference-faithful "

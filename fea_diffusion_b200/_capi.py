@@ -64,6 +64,7 @@ class SolveStats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("cluster_systems", C.c_int32), ("cluster_count", C.c_int32), ("cluster_iterations", C.c_int64),
         ("cluster_ms", C.c_float), ("cluster_size", C.c_int32),
+        ("refined_systems", C.c_int32), ("pad_", C.c_int32),
     ]
 
     def as_dict(self):

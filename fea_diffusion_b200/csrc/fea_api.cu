@@ -196,6 +196,7 @@ int fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other) {
 int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return FEA_BAD_ARG;
   if (strcmp(key, "pcg_path") == 0) ctx->c.pcg_path = value == 1 ? 1 : 0;
+  else if (strcmp(key, "refine_rounds") == 0) ctx->c.refine_rounds = value < 0 ? 0 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;
   else if (strcmp(key, "use_graphs") == 0) ctx->c.use_graphs = value ? 1 : 0;
   else return fail(ctx, FEA_BAD_ARG, "unknown option key");

@@ -35,6 +35,7 @@ struct Ctx {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;  // around the cluster-path kernel
   int use_graphs = 1;                  // env FEA_NO_GRAPHS=1 disables
+  int refine_rounds = 2;               // true-residual checks (residual replacement) per solve; 0 = off
   int pcg_path = 0;                    // 0 = auto (on-chip cluster kernel where systems fit), 1 = streaming only
   int cluster_capacity[2] = {-1, -1};  // co-resident clusters of 4 / 8 CTAs (-1 = not queried yet)
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default

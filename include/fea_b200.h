@@ -106,6 +106,10 @@ typedef struct fea_solve_stats {
   int64_t cluster_iterations;  /* sum of their iteration counts */
   float   cluster_ms;          /* CUDA-event duration of that kernel */
   int32_t cluster_size;        /* CTAs per cluster (4 or 8) of the class that solved most systems */
+  /* residual replacement: systems whose TRUE residual b - K x missed the tolerance after the
+   * recursive one had met it, and that were therefore restarted from their current x */
+  int32_t refined_systems;
+  int32_t pad_;
 } fea_solve_stats;
 
 /* ---- library / context -------------------------------------------------- */
@@ -128,7 +132,8 @@ int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_sto
  * has finished (same device): joins several contexts' streams for one event-timed region */
 int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
 /* integer options: "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
- * the streaming kernels; "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
+ * the streaming kernels; "refine_rounds" true-residual checks per solve (default 2, 0 = off);
+ * "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
 int  fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this context has launched so far (graph nodes included) */
 int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
