@@ -27,7 +27,7 @@ EXPORTS = [
 ]
 
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "CUDA_ERROR", 3: "OUT_OF_MEMORY", 4: "BAD_STATE", 5: "MESH_ERROR"}
-SAMPLE_NOT_RUN, SAMPLE_CONVERGED, SAMPLE_MAX_ITER, SAMPLE_BREAKDOWN, SAMPLE_EMPTY_ROW = -1, 0, 1, 2, 3
+SAMPLE_NOT_RUN, SAMPLE_CONVERGED, SAMPLE_MAX_ITER, SAMPLE_BREAKDOWN, SAMPLE_EMPTY_ROW, SAMPLE_STAGNATED = -1, 0, 1, 2, 3, 4
 
 
 class FeaError(RuntimeError):

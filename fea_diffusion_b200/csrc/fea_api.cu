@@ -281,7 +281,7 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(dalloc(b, &b.err_flag, 4));
   A(dalloc(b, &b.empty, ns));
   A(dalloc(b, &b.cl_order, ns));
-  A(dalloc(b, &b.cl_counter, 2));
+  A(dalloc(b, &b.cl_counter, 4));   // queue heads of the two cluster classes, restart count, scratch
   if (!order.empty()) A(cudaMemcpyAsync(b.cl_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
   A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
   A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));
@@ -368,6 +368,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.sc.tol2, b.ns));
   CK(ctx, dalloc(b, &b.sc.done, b.ns));
   CK(ctx, dalloc(b, &b.sc.iters, b.ns));
+  CK(ctx, dalloc(b, &b.sc.cap, b.ns));
   CK(ctx, dalloc(b, &b.sc.status, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumA, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumB, b.ns));

@@ -35,7 +35,7 @@ struct Ctx {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;  // around the cluster-path kernel
   int use_graphs = 1;                  // env FEA_NO_GRAPHS=1 disables
-  int refine_rounds = 2;               // true-residual checks (residual replacement) per solve; 0 = off
+  int refine_rounds = 1;               // restarts from the true residual per solve (0 = check only)
   int pcg_path = 0;                    // 0 = auto (on-chip cluster kernel where systems fit), 1 = streaming only
   int cluster_capacity[2] = {-1, -1};  // co-resident clusters of 4 / 8 CTAs (-1 = not queried yet)
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
@@ -50,6 +50,7 @@ struct SysScalars {
   double* tol2;      // rtol^2 * rz0
   int32_t* done;     // 0 = iterating, 1 = finished
   int32_t* iters;
+  int32_t* cap;      // iteration budget of the current (re)start; < max_iter only after a reopen
   int32_t* status;
   double* psumA;     // per-system sums of the CTA partials (two-level mode, huge systems only)
   double* psumB;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
     int st = -1;
     if (!isfinite(rz)) st = FEA_SAMPLE_BREAKDOWN;
     else if (rz <= P.sc.tol2[s]) st = FEA_SAMPLE_CONVERGED;
-    else if (P.sc.iters[s] >= P.max_iter) st = FEA_SAMPLE_MAX_ITER;
+    else if (P.sc.iters[s] >= P.sc.cap[s]) st = P.sc.cap[s] < P.max_iter ? FEA_SAMPLE_STAGNATED : FEA_SAMPLE_MAX_ITER;
     if (st >= 0) {  // every CTA of the system takes the same decision; the leader records it
       if (leader) {
         P.sc.done[s] = 1;
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
   const int cta = blockIdx.x;
   const int s = P.sys_of_cta[cta];
   if (s < 0) return;
-  if (P.sc.status[s] != FEA_SAMPLE_CONVERGED || P.sc.iters[s] == 0) return;
+  const int st = P.sc.status[s];
+  if ((st != FEA_SAMPLE_CONVERGED && st != FEA_SAMPLE_STAGNATED) || P.sc.iters[s] == 0 || P.sc.cap[s] < 0) return;
   const int64_t row = (int64_t)cta * kT + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int64_t slice = row >> 5;
@@ -241,17 +242,28 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
 }
 
 // one warp per system; reopened systems restart CG (beta = 0) from their current x
-__global__ void k_pcg_refine_scalars(const PcgPtrs* __restrict__ Pp, int32_t* __restrict__ n_reopened) {
+__global__ void k_pcg_refine_scalars(const PcgPtrs* __restrict__ Pp, int32_t* __restrict__ n_reopened, int allow_reopen) {
   const PcgPtrs& P = *Pp;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= P.ns) return;
-  if (P.sc.status[s] != FEA_SAMPLE_CONVERGED || P.sc.iters[s] == 0) return;
+  const int st = P.sc.status[s];
+  if ((st != FEA_SAMPLE_CONVERGED && st != FEA_SAMPLE_STAGNATED) || P.sc.iters[s] == 0 || P.sc.cap[s] < 0) return;
   const double total = sum_partials(P.partB + P.cta_first[s], P.cta_count[s]);
   if ((threadIdx.x & 31) != 0) return;
   P.rz_last[s] = total;                       // what relres reports: the true residual
+  if (st == FEA_SAMPLE_STAGNATED) return;
   // restart only when the gap is material (true residual more than 10x the tolerance): a restart
   // costs the Krylov space, and errors against a direct solve are already ~1e-10 at this level
-  if (total > 100.0 * P.sc.tol2[s] && isfinite(total) && P.sc.iters[s] < P.max_iter) {
+  if (!(total > 100.0 * P.sc.tol2[s] && isfinite(total))) return;
+  if (!allow_reopen || P.sc.iters[s] >= P.max_iter) {
+    P.sc.status[s] = FEA_SAMPLE_STAGNATED;
+    return;
+  }
+  {
+    // a restart that cannot close the gap (attainable accuracy ~ eps * cond) must not run away
+    const int it = P.sc.iters[s];
+    const int cap = it + it / 4 + 100;
+    P.sc.cap[s] = cap < P.max_iter ? cap : P.max_iter;
     P.sc.rz[0][s] = total;
     P.sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);  // +inf -> beta = 0
     P.sc.psumB[s] = total;
@@ -358,6 +370,7 @@ __global__ void k_pcg_init_scalars(const PcgPtrs* __restrict__ Pp, const int32_t
   P.sc.psumA[s] = 1.0;
   P.sc.psumB[s] = total;
   P.sc.iters[s] = 0;
+  P.sc.cap[s] = P.max_iter;
   int st = FEA_SAMPLE_NOT_RUN, dn = 0;
   if (empty[s]) { st = FEA_SAMPLE_EMPTY_ROW; dn = 1; }
   else if (!(total > 0.0)) { st = isfinite(total) ? FEA_SAMPLE_CONVERGED : FEA_SAMPLE_BREAKDOWN; dn = 1; }
@@ -468,7 +481,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
   if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
-    cudaMemsetAsync(b.cl_counter, 0, 2 * sizeof(int32_t), st);
+    cudaMemsetAsync(b.cl_counter, 0, 4 * sizeof(int32_t), st);
     cudaEventRecord(c.ev_c0, st);
     for (int k = 1; k >= 0; --k) {   // the few large systems (8-CTA clusters) first
       if (!P.cl_cnt[k]) continue;
@@ -483,13 +496,13 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   std::vector<int> done_after;  // finished systems observed after chunk k
   int timed = 0, k = 0, reopened_total = 0;
   const int max_chunks = (max_iter + kChunk - 1) / kChunk + 2;
-  for (int round = 0; ncta && round <= c.refine_rounds; ++round) {
+  for (int round = 0; ncta && round <= c.refine_rounds + 1; ++round) {
     if (round > 0) {
       // residual replacement: check converged systems against their true residual, reopen failures
-      int32_t* d_reopened = b.cl_counter;   // reuse the queue counters as scratch
+      int32_t* d_reopened = b.cl_counter + 3;
       cudaMemsetAsync(d_reopened, 0, sizeof(int32_t), st);
       k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
-      k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened);
+      k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened, round <= c.refine_rounds ? 1 : 0);
       k_compact_active<<<1, 1024, 0, st>>>(dP);
       launches += 3;
       int32_t h_reopened = 0;
@@ -498,7 +511,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       reopened_total += h_reopened;
       if (h_reopened == 0) break;
     } else if (n_cluster >= b.ns) {
-      continue;   // everything was solved on chip: go straight to the true-residual check
+      break;      // everything was solved AND verified against its true residual on chip
     }
     int n_active = ncta;  // stale upper bound of the work-list length
     const int k_end = k + max_chunks;
@@ -536,7 +549,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // the polls lag one chunk
   }
-  b.stats.refined_systems = reopened_total;
+  b.stats.refined_systems += reopened_total;
   if ((e = launch_finalize(b)) != cudaSuccess) return e;
   launches += 3;
   if ((e = cudaEventRecord(c.ev_t1, st)) != cudaSuccess) return e;
@@ -568,6 +581,9 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     b.stats.cluster_count = nclusters;
     b.stats.cluster_iterations = tot;
     cudaEventElapsedTime(&b.stats.cluster_ms, c.ev_c0, c.ev_c1);
+    int32_t h_restarts = 0;
+    if ((e = cudaMemcpy(&h_restarts, b.cl_counter + 2, sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    b.stats.refined_systems += h_restarts;
 #ifdef FEA_CLUSTER_PROFILE
     pcg_cluster_profile_dump();
 #endif
@@ -728,6 +744,7 @@ __global__ void k_spmv_scalars(int ns, SysScalars sc, const int32_t* __restrict_
   sc.rz[1][s] = __longlong_as_double(0x7ff0000000000000LL);  // beta = 0: p = r
   sc.done[s] = 0;
   sc.iters[s] = 0;
+  sc.cap[s] = 1 << 30;
   sc.tol2[s] = 0.0;
   sc.psumB[s] = 1.0;
   for (int i = 0; i < cta_count[s]; ++i) partB[cta_first[s] + i] = 1.0;  // "not converged"

@@ -51,8 +51,11 @@ enum fea_sample_status {
   FEA_SAMPLE_CONVERGED = 0,
   FEA_SAMPLE_MAX_ITER = 1,   /* not converged within max_iter */
   FEA_SAMPLE_BREAKDOWN = 2,  /* p^T A p <= 0 or non-finite: matrix not SPD (floating region, F4) */
-  FEA_SAMPLE_EMPTY_ROW = 3   /* an active vertex touches no stiffness cell: exactly singular
+  FEA_SAMPLE_EMPTY_ROW = 3,  /* an active vertex touches no stiffness cell: exactly singular
                                 (the reference's SuperLU-NaN -> calculate() False path, A-18) */
+  FEA_SAMPLE_STAGNATED = 4   /* the recursive residual met rtol but the true residual b - K x stays
+                                above 10 rtol even after a restart: too ill-conditioned for fp64 CG at
+                                this tolerance; u is the best iterate, relres its TRUE residual */
 };
 
 /*
@@ -132,7 +135,8 @@ int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_sto
  * has finished (same device): joins several contexts' streams for one event-timed region */
 int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
 /* integer options: "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
- * the streaming kernels; "refine_rounds" true-residual checks per solve (default 2, 0 = off);
+ * the streaming kernels; "refine_rounds" restarts from the true residual per solve (default 1;
+ * 0 = the true residual is only checked and reported);
  * "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
 int  fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this context has launched so far (graph nodes included) */

@@ -8,7 +8,7 @@ import cases
 from fea_diffusion_b200 import Context, FeaError, Sample, pack
 from fea_diffusion_b200 import imaging
 from fea_diffusion_b200._capi import (SAMPLE_BREAKDOWN, SAMPLE_CONVERGED, SAMPLE_EMPTY_ROW,
-                                      SAMPLE_MAX_ITER)
+                                      SAMPLE_MAX_ITER, SAMPLE_STAGNATED)
 from oracle import raster_oracle as ro
 from oracle.fea_oracle import element_stiffness
 
@@ -209,7 +209,7 @@ def test_singular_samples_are_reported(ctx):
     with ctx.create_batch(pack([setup.sample, lonely, good.sample])) as b:
         r = b.assemble().solve(1e-10, 3000).download()
         us = b.packed.split_vertices(r.u)
-    assert r.status[0] in (SAMPLE_BREAKDOWN, SAMPLE_MAX_ITER)
+    assert r.status[0] in (SAMPLE_BREAKDOWN, SAMPLE_MAX_ITER, SAMPLE_STAGNATED)
     assert r.status[1] == SAMPLE_EMPTY_ROW and np.isnan(us[1]).all()
     assert r.status[2] == SAMPLE_CONVERGED and np.isfinite(us[2]).all()
 
