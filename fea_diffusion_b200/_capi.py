@@ -20,7 +20,7 @@ EXPORTS = [
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
     "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
-    "fea_batch_download_images", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
+    "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
     "fea_batch_get_timed_launches",
     "fea_batch_sample_sizes", "fea_batch_get_conn", "fea_batch_get_element_stiffness",
     "fea_batch_get_csr", "fea_batch_spmv", "fea_rasterize_fields", "fea_solve_batch",
@@ -115,6 +115,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_get_csr": (C.c_int, [P, I32, P, P, P]),
         "fea_batch_spmv": (C.c_int, [P, I32, P, P]),
         "fea_batch_cell_strain_stress": (C.c_int, [P, I32, P, P]),
+        "fea_batch_rasterize_flags": (C.c_int, [P, P, P, P]),
         "fea_rasterize_fields": (C.c_int, [P, P, C.c_int64, P, C.c_int64, I32, P, I32, I32, P, P, I32, P]),
         "fea_solve_batch": (C.c_int, [P, C.POINTER(BatchDesc), F64, I32, I32, P, F64, P, P, P, P, P, P,
                                       C.POINTER(SolveStats)]),

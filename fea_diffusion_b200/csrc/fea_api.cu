@@ -436,6 +436,39 @@ int fea_batch_download(fea_batch* hb, double* u, double* ranges, int32_t* iters,
   return FEA_OK;
 }
 
+int fea_batch_rasterize_flags(fea_batch* hb, const int64_t* field_off, const uint8_t* flags, uint8_t* images) {
+  if (!hb || !field_off || !flags || !images) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.rasterized) return fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize_flags before fea_batch_rasterize");
+  if (field_off[0] != 0) return fail(ctx, FEA_BAD_ARG, "field_off must start at 0");
+  std::vector<int64_t> flag_off(b.ns + 1, 0);
+  for (int s = 0; s < b.ns; ++s) {
+    if (field_off[s + 1] < field_off[s]) return fail(ctx, FEA_BAD_ARG, "field_off must be non-decreasing");
+    flag_off[s + 1] = flag_off[s] + (field_off[s + 1] - field_off[s]) * (b.vtx_off[s + 1] - b.vtx_off[s]);
+  }
+  const int64_t n_img = field_off[b.ns], n_flags = flag_off[b.ns];
+  if (n_img == 0) return FEA_OK;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  const size_t per = (size_t)b.img_size * b.img_size, tab = sizeof(int64_t) * (b.ns + 1);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_fo = 0, o_go = up(tab), o_fl = o_go + up(tab), o_im = o_fl + up((size_t)n_flags), total = o_im + up(n_img * per);
+  char* d = nullptr;
+  CK(ctx, cudaMallocAsync((void**)&d, total, st));
+  cudaError_t e = cudaMemcpyAsync(d + o_fo, field_off, tab, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_go, flag_off.data(), tab, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_fl, flags, (size_t)n_flags, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_raster_flags(b, n_img, (const int64_t*)(d + o_fo), (const int64_t*)(d + o_go),
+                                                (const uint8_t*)(d + o_fl), (uint8_t*)(d + o_im));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(images, d + o_im, n_img * per, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // flag_off (host vector) must outlive the copy
+  cudaFreeAsync(d, st);
+  ctx->c.launches += 1;
+  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_rasterize_flags", e);
+  return FEA_OK;
+}
+
 int fea_batch_cell_strain_stress(fea_batch* hb, int32_t stress_region, double* strain, double* stress) {
   if (!hb || (!strain && !stress)) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;

@@ -254,6 +254,18 @@ class Batch:
         r.stats = self.stats()
         return r
 
+    def rasterize_flags(self, flags_per_sample: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """Region images of every sample: ``flags_per_sample[s]`` is (n_regions_s, n_vertices_s)
+        bool/uint8; returns one (n_regions_s, size, size) uint8 array per sample."""
+        counts = [len(f) for f in flags_per_sample]
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.uint8).reshape(-1) for f in flags_per_sample]
+                                                   or [np.zeros(0, np.uint8)]))
+        out = np.empty((int(off[-1]), self.image_size, self.image_size), np.uint8)
+        if off[-1]:
+            self.ctx._check(self.ctx.lib.fea_batch_rasterize_flags(self.h, ptr(off), ptr(flat), ptr(out)))
+        return [out[off[s]:off[s + 1]] for s in range(len(counts))]
+
     def cell_strain_stress(self, stress_region: int = -1):
         """(strain, stress), each (n_cells, 3): final-step cell averages (e11, e22, 2e12), D*strain."""
         nc = len(self.packed.conn)

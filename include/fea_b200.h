@@ -171,6 +171,12 @@ int  fea_batch_destroy(fea_batch* b);
 int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
                         double* relres, int32_t* status);
 int  fea_batch_download_images(fea_batch* b, uint8_t* images);
+/* Region images of every sample (regions_<Region>.png, fea_analysis.py:508-524) with the camera of
+ * the preceding fea_batch_rasterize: sample s has field_off[s+1]-field_off[s] regions; flags holds,
+ * sample after sample, one uint8 per (region, vertex) (1 = vertex in the region); images
+ * [field_off[n]][size][size] uint8: the 0/1 flag interpolated over each triangle, black = 1. */
+int  fea_batch_rasterize_flags(fea_batch* b, const int64_t* field_off, const uint8_t* flags,
+                               uint8_t* images);
 /* Final-step cell averages written into domain.<k>.vtk by the reference's post-process hook
  * (ev_cauchy_strain / ev_cauchy_stress 'el_avg', fea_analysis.py:397-416): strain [n_cells*3] =
  * (e11, e22, 2e12), stress [n_cells*3] = D * strain.  stress_region >= 0: material-table entry of

@@ -144,3 +144,53 @@ def test_generate_data_tree(tmp_path):
             lo, hi = eval(lines[-2].split(":", 1)[1])
             assert lo == p4["u"][:, 0].min() and hi == p4["u"][:, 0].max()
     assert len(co) == len(p4["u"])
+
+
+def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
+    """fea_diffusion_b200.dataset.generate_dataset (batched, pipelined) against FEAnalysis on the
+    same plates: same files, same pixels, same ranges; shards of a 2-rank run are identical to
+    the 1-rank run."""
+    from fea_diffusion_b200.dataset import generate_dataset
+    from fea_diffusion_b200.workload import plate_conditions
+    kw = dict(conditions_per_plate=2, image_size=64, num_steps=5, mesh_size=5e-2, seed=7, plates_per_batch=2,
+              workers=2, save_meshes=True)
+    d1 = str(tmp_path / "one")
+    st = generate_dataset(d1, 3, **kw)
+    assert st["plates"] == 3 and st["samples"] == 6
+    d2 = str(tmp_path / "two")
+    for rank in range(2):
+        generate_dataset(d2, 3, rank=rank, world=2, device=0, **kw)
+    for plate in ("1", "2", "3"):
+        for root, _, files in os.walk(os.path.join(d1, plate)):
+            for f in files:
+                a = open(os.path.join(root, f), "rb").read()
+                b = open(os.path.join(root.replace(d1, d2), f), "rb").read()
+                assert a == b, (root, f)
+    # plate 2 through the drop-in class
+    items, _ = plate_conditions(7 + 1, 2, 64, mesh_size=5e-2)
+    data_dir = str(tmp_path / "ref")
+    os.makedirs(data_dir)
+    write_medit(os.path.join(data_dir, "part.mesh"), items[0].setup.coors, items[0].setup.conn)
+    for ci, it in enumerate(items):
+        cond_dir = os.path.join(data_dir, str(ci + 1))
+        os.makedirs(cond_dir)
+        an = FEAnalysis("part.mesh", data_dir, cond_dir, num_steps=5, **it.kwargs)
+        assert an.calculate()
+        an.update_image_size_or_bounds(image_size=it.window, bounds=it.bounds)
+        an.save_region_images(os.path.join(cond_dir, "regions"))
+        an.save_output_images(os.path.join(cond_dir, "outputs"), save_stress=False, save_strain=False)
+        got = os.path.join(d1, "2", str(ci + 1))
+        for f in sorted(os.listdir(cond_dir)):
+            if f.endswith(".png"):
+                x = np.array(Image.open(os.path.join(cond_dir, f))).astype(int)
+                y = np.array(Image.open(os.path.join(got, f))).astype(int)
+                assert x.shape == y.shape and np.abs(x - y).max() <= 1, f
+            elif f in ("magnitudes.txt", "materials.txt"):
+                assert open(os.path.join(cond_dir, f)).read() == open(os.path.join(got, f)).read()
+        ra = [eval(l.split(":", 1)[1]) for l in open(os.path.join(cond_dir, "ranges.txt"))]
+        rb = [eval(l.split(":", 1)[1]) for l in open(os.path.join(got, "ranges.txt"))]
+        assert np.allclose(ra, rb, rtol=1e-12, atol=0)
+        _, _, pd, cd = read_vtk(os.path.join(got, "domain.4.vtk"))
+        assert np.allclose(pd["u"][:, :2], an.displacement[-1], rtol=1e-9, atol=1e-18)
+        assert np.allclose(cd["cauchy_strain"], an.cell_strain, rtol=1e-9, atol=1e-18)
+    assert np.array_equal(np.array(Image.open(os.path.join(d1, "2", "input.png")).size), [items[0].size] * 2)
