@@ -117,7 +117,7 @@ def _write_plate(data_dir, job, res, num_steps, save_meshes):
 
 def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int = 4, image_size: int = 64,
                      num_steps: int = 11, mesh_size: float = 1e-2, seed: int = 0, rank: int = 0, world: int = 1,
-                     device: Optional[int] = None, plates_per_batch: int = 25, workers: Optional[int] = None,
+                     device: Optional[int] = None, plates_per_batch: int = 50, workers: Optional[int] = None,
                      writer_threads: int = 8, save_meshes: bool = False, well_posed: bool = True,
                      start_plate: int = 0, rtol: float = 1e-10, max_iter: int = 50000,
                      progress: Optional[Callable[[int, int], None]] = None) -> Dict:
@@ -133,46 +133,47 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
     pending = []
 
     def run_batch(jobs: List[dict], writers: ThreadPoolExecutor):
-        sizes = {j["size"] for j in jobs}
-        by_size = {sz: [j for j in jobs if j["size"] == sz] for sz in sizes}   # crop sizes differ by +-1 px
-        for sz, group in by_size.items():
-            samples = [c["sample"] for j in group for c in j["conds"]]
-            affine = np.stack([j["affine"] for j in group for _ in j["conds"]])
-            packed = pack(samples)
-            t0 = time.perf_counter()
-            with ctx.create_batch(packed) as b:
-                b.assemble().solve(rtol, max_iter).rasterize(sz, affine, t1)
-                res = b.download(images=True)
-                flags = []
-                for j in group:
-                    for ci, c in enumerate(j["conds"]):
-                        f = c["flags"]
-                        if ci == 0:   # the plate mask (input.png) rides along as one more field
-                            f = np.concatenate([f, np.ones((1, f.shape[1]), np.uint8)])
-                        flags.append(f)
-                region_imgs = b.rasterize_flags(flags)
-                conn, _ = b.conn() if save_meshes else (None, None)
-                strain, stress = b.cell_strain_stress(0) if save_meshes else (None, None)
-            stats["gpu_s"] += time.perf_counter() - t0
-            us = packed.split_vertices(res.u)
-            k = 0
-            for j in group:
-                out = dict(conds=[])
+        # crop sizes differ by +-1 px between plates: render the batch at the largest size (the affine
+        # maps are relative to each crop's origin) and cut every sample's top-left square out of it
+        sz = max(j["size"] for j in jobs)
+        samples = [c["sample"] for j in jobs for c in j["conds"]]
+        affine = np.stack([j["affine"] for j in jobs for _ in j["conds"]])
+        packed = pack(samples)
+        t0 = time.perf_counter()
+        with ctx.create_batch(packed) as b:
+            b.assemble().solve(rtol, max_iter).rasterize(sz, affine, t1)
+            res = b.download(images=True)
+            flags = []
+            for j in jobs:
                 for ci, c in enumerate(j["conds"]):
-                    reg = region_imgs[k]
-                    if ci == 0:
-                        out["input"] = reg[-1]
-                        reg = reg[:-1]
-                    d = dict(images=res.images[k], regions=reg, ranges=res.ranges[k], status=int(res.status[k]),
-                             iters=int(res.iters[k]), relres=float(res.relres[k]))
-                    if save_meshes:
-                        c0, c1 = packed.cell_off[k], packed.cell_off[k + 1]
-                        d.update(u=us[k], conn=conn[c0:c1], strain=strain[c0:c1], stress=stress[c0:c1])
-                    stats["not_converged"] += int(res.status[k] != SAMPLE_CONVERGED)
-                    out["conds"].append(d)
-                    k += 1
-                pending.append(writers.submit(_write_plate, data_dir, j, out, num_steps, save_meshes))
-            stats["batches"] += 1
+                    f = c["flags"]
+                    if ci == 0:   # the plate mask (input.png) rides along as one more field
+                        f = np.concatenate([f, np.ones((1, f.shape[1]), np.uint8)])
+                    flags.append(f)
+            region_imgs = b.rasterize_flags(flags)
+            conn, _ = b.conn() if save_meshes else (None, None)
+            strain, stress = b.cell_strain_stress(0) if save_meshes else (None, None)
+        stats["gpu_s"] += time.perf_counter() - t0
+        us = packed.split_vertices(res.u)
+        k = 0
+        for j in jobs:
+            out = dict(conds=[])
+            n = j["size"]
+            for ci, c in enumerate(j["conds"]):
+                reg = region_imgs[k][:, :n, :n]
+                if ci == 0:
+                    out["input"] = reg[-1]
+                    reg = reg[:-1]
+                d = dict(images=res.images[k][:, :n, :n], regions=reg, ranges=res.ranges[k], status=int(res.status[k]),
+                         iters=int(res.iters[k]), relres=float(res.relres[k]))
+                if save_meshes:
+                    c0, c1 = packed.cell_off[k], packed.cell_off[k + 1]
+                    d.update(u=us[k], conn=conn[c0:c1], strain=strain[c0:c1], stress=stress[c0:c1])
+                stats["not_converged"] += int(res.status[k] != SAMPLE_CONVERGED)
+                out["conds"].append(d)
+                k += 1
+            pending.append(writers.submit(_write_plate, data_dir, j, out, num_steps, save_meshes))
+        stats["batches"] += 1
 
     jobs_args = [(p, seed, conditions_per_plate, image_size, mesh_size, well_posed) for p in mine]
     ctx = None

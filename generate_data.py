@@ -41,7 +41,7 @@ def parse(argv=None):
     ap.add_argument("--backend", choices=["batched", "dropin"], default="batched")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the plates over (batched).")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--plates_per_batch", type=int, default=25)
+    ap.add_argument("--plates_per_batch", type=int, default=50)
     ap.add_argument("--rank", type=int, default=None, help=argparse.SUPPRESS)   # set for the per-GPU children
     return ap.parse_args(argv)
 
