@@ -289,15 +289,16 @@ def run_b200(a):
         alg_bytes = float((res0.iters.astype(np.float64) * b_iter).sum())
         ms = float(np.mean([s["cluster_ms"] for s in stats]))
         achieved = alg_bytes / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_pcg_cluster<%d>" % cl_size,
+        roofline = {"bound": "hbm", "kernel": "k_pcg_cluster<1..8> (one persistent kernel per cluster size, launched "
+                                              "concurrently; most systems ran on %d-CTA clusters)" % cl_size,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(info, "cluster_traffic.json"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms,
                     "timed_launches": len(stats), "pcg_iterations_in_launch": int(res0.iters.sum()),
-                    "regime": "on-chip: each system's matrix is read from HBM once per solve into the shared memory of a "
-                              "%d-CTA cluster and its CG vectors stay in registers, so achieved algorithmic GB/s exceeds the "
-                              "HBM peak by design; HBM-streaming figures of the same iterations are in 'streaming_path'"
-                              % cl_size,
+                    "regime": "on-chip: each system's matrix is read from HBM once per solve into the shared memory (and L2) "
+                              "of a thread-block cluster and its CG vectors stay in registers, so achieved algorithmic GB/s "
+                              "exceeds the HBM peak by design; HBM-streaming figures of the same iterations are in "
+                              "'streaming_path'",
                     "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"]}
     else:
         roofline = None

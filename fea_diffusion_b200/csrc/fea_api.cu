@@ -108,6 +108,7 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   if (const char* v = getenv("FEA_NO_GRAPHS")) ctx->c.use_graphs = atoi(v) ? 0 : 1;
+  if (const char* v = getenv("FEA_CLUSTER_MIN")) ctx->c.cluster_min = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("FEA_PCG_PATH")) ctx->c.pcg_path = (strcmp(v, "stream") == 0 || atoi(v) == 1) ? 1 : 0;
   if (cudaHostAlloc((void**)&ctx->c.h_flag, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
       cudaMalloc(&ctx->c.d_pcg_params, kPcgParamBytes) != cudaSuccess) {
@@ -121,6 +122,11 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   cudaEventCreateWithFlags(&ctx->c.ev_poll[1], cudaEventDisableTiming);
   cudaEventCreate(&ctx->c.ev_t0);
   cudaEventCreate(&ctx->c.ev_t1);
+  cudaEventCreateWithFlags(&ctx->c.ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < 3; ++i) {
+    cudaStreamCreateWithPriority(&ctx->c.aux[i], cudaStreamNonBlocking, priority);
+    cudaEventCreateWithFlags(&ctx->c.ev_join[i], cudaEventDisableTiming);
+  }
   cudaEventCreate(&ctx->c.ev_c0);
   cudaEventCreate(&ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
@@ -141,6 +147,11 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaEventDestroy(ctx->c.ev_poll[1]);
   cudaEventDestroy(ctx->c.ev_t0);
   cudaEventDestroy(ctx->c.ev_t1);
+  cudaEventDestroy(ctx->c.ev_fork);
+  for (int i = 0; i < 3; ++i) {
+    cudaEventDestroy(ctx->c.ev_join[i]);
+    if (ctx->c.aux[i]) cudaStreamDestroy(ctx->c.aux[i]);
+  }
   cudaEventDestroy(ctx->c.ev_c0);
   cudaEventDestroy(ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
@@ -196,6 +207,7 @@ int fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other) {
 int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return FEA_BAD_ARG;
   if (strcmp(key, "pcg_path") == 0) ctx->c.pcg_path = value == 1 ? 1 : 0;
+  else if (strcmp(key, "cluster_min") == 0) ctx->c.cluster_min = value < 1 ? 1 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "refine_rounds") == 0) ctx->c.refine_rounds = value < 0 ? 0 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;
   else if (strcmp(key, "use_graphs") == 0) ctx->c.use_graphs = value ? 1 : 0;
@@ -245,10 +257,10 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   }
   // on-chip solver path: every system is assigned a cluster class by its own size alone
   std::vector<int32_t> order;
-  for (int cls = 0; cls < 2; ++cls) {
+  for (int cls = 1; cls <= 8; ++cls) {
     b.cl_off[cls] = (int32_t)order.size();
     for (int s = 0; s < ns; ++s)
-      if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s]) == cls) order.push_back(s);
+      if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s], ctx->c.cluster_min) == cls) order.push_back(s);
     b.cl_cnt[cls] = (int32_t)order.size() - b.cl_off[cls];
     std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) {
       return b.vtx_off[x + 1] - b.vtx_off[x] > b.vtx_off[y + 1] - b.vtx_off[y];
@@ -281,7 +293,7 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(dalloc(b, &b.err_flag, 4));
   A(dalloc(b, &b.empty, ns));
   A(dalloc(b, &b.cl_order, ns));
-  A(dalloc(b, &b.cl_counter, 4));   // queue heads of the two cluster classes, restart count, scratch
+  A(dalloc(b, &b.cl_counter, 16));  // queue heads of the cluster classes, restart count, scratch
   if (!order.empty()) A(cudaMemcpyAsync(b.cl_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
   A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
   A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));

@@ -37,7 +37,10 @@ struct Ctx {
   int use_graphs = 1;                  // env FEA_NO_GRAPHS=1 disables
   int refine_rounds = 1;               // restarts from the true residual per solve (0 = check only)
   int pcg_path = 0;                    // 0 = auto (on-chip cluster kernel where systems fit), 1 = streaming only
-  int cluster_capacity[2] = {-1, -1};  // co-resident clusters of 4 / 8 CTAs (-1 = not queried yet)
+  int cluster_capacity[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // co-resident clusters of c CTAs (-1 = not queried)
+  int cluster_min = 1;                 // smallest cluster size used (1..8)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // cluster kernels of different classes run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
   int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };
@@ -92,8 +95,8 @@ struct Batch {
   int32_t max_cta_count = 0;         // host copy: most CTAs any one system owns
   int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
   int32_t* cl_order = nullptr;       // [ns] systems of the cluster path: class 0 then class 1
-  int32_t cl_off[2] = {0, 0}, cl_cnt[2] = {0, 0};
-  int32_t* cl_counter = nullptr;     // [2] device work-queue heads
+  int32_t cl_off[9] = {}, cl_cnt[9] = {};   // index = CTAs per cluster
+  int32_t* cl_counter = nullptr;     // [16] device work-queue heads [1..8], restart count [0], scratch [9]
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending
@@ -146,10 +149,10 @@ cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d
 // whole lock-step PCG loop (init, chunks of kChunk iterations, polling); fills b.stats / timings
 cudaError_t run_pcg(Batch& b, double rtol, int max_iter);
 void pcg_release(Ctx& c);                                     // destroys the cached graphs
-int pcg_cluster_class(int64_t n_vertices_of_sample);          // 0: 4-CTA cluster, 1: 8-CTA, -1: streaming
+int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl);  // CTAs per cluster (1..8), 0: streaming
 int pcg_cluster_capacity(Ctx& c, int cl);                     // co-resident clusters (0 = unavailable)
 struct PcgPtrs;
-cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl);
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st);
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);

@@ -403,7 +403,7 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   P.max_iter = max_iter;
   P.two_level = b.max_cta_count > kDirectSumMax ? 1 : 0;
   P.cl_order = b.cl_order;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 9; ++k) {
     P.cl_off[k] = b.cl_off[k];
     P.cl_cnt[k] = b.cl_cnt[k];
   }
@@ -463,8 +463,9 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   PcgPtrs* dP = (PcgPtrs*)c.d_pcg_params;
   PcgPtrs P = make_ptrs(b, max_iter);
   int n_cluster = 0;
-  for (int k = 0; k < 2; ++k) {
-    if (c.pcg_path != 0 || pcg_cluster_capacity(c, k ? 8 : 4) <= 0) P.cl_cnt[k] = 0;
+  P.cl_cnt[0] = 0;
+  for (int k = 1; k <= 8; ++k) {
+    if (c.pcg_path != 0 || (P.cl_cnt[k] && pcg_cluster_capacity(c, k) <= 0)) P.cl_cnt[k] = 0;
     n_cluster += P.cl_cnt[k];
   }
   const bool two = P.two_level != 0;
@@ -481,12 +482,31 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
   if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
-    cudaMemsetAsync(b.cl_counter, 0, 4 * sizeof(int32_t), st);
+    cudaMemsetAsync(b.cl_counter, 0, 16 * sizeof(int32_t), st);
     cudaEventRecord(c.ev_c0, st);
-    for (int k = 1; k >= 0; --k) {   // the few large systems (8-CTA clusters) first
+    // one persistent kernel per cluster class, largest clusters first; classes are spread over the
+    // main stream and three auxiliary streams so that their clusters are co-scheduled and small
+    // clusters fill the SMs that larger ones cannot use (GPC granularity)
+    cudaEventRecord(c.ev_fork, st);
+    bool used[3] = {false, false, false};
+    int slot = 0;
+    for (int k = 8; k >= 1; --k) {
       if (!P.cl_cnt[k]) continue;
-      if ((e = launch_pcg_cluster(c, dP, P.cl_cnt[k], k ? 8 : 4)) != cudaSuccess) return e;
+      cudaStream_t ks = st;
+      if (slot > 0 && c.aux[(slot - 1) % 3]) {
+        const int a = (slot - 1) % 3;
+        ks = c.aux[a];
+        if (!used[a]) cudaStreamWaitEvent(ks, c.ev_fork, 0);
+        used[a] = true;
+      }
+      if ((e = launch_pcg_cluster(c, dP, P.cl_cnt[k], k, ks)) != cudaSuccess) return e;
       launches += 1;
+      ++slot;
+    }
+    for (int a = 0; a < 3; ++a) {
+      if (!used[a]) continue;
+      cudaEventRecord(c.ev_join[a], c.aux[a]);
+      cudaStreamWaitEvent(st, c.ev_join[a], 0);
     }
     cudaEventRecord(c.ev_c1, st);
   }
@@ -499,7 +519,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   for (int round = 0; ncta && round <= c.refine_rounds + 1; ++round) {
     if (round > 0) {
       // residual replacement: check converged systems against their true residual, reopen failures
-      int32_t* d_reopened = b.cl_counter + 3;
+      int32_t* d_reopened = b.cl_counter + 9;
       cudaMemsetAsync(d_reopened, 0, sizeof(int32_t), st);
       k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
       k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened, round <= c.refine_rounds ? 1 : 0);
@@ -567,22 +587,24 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   b.stats.iterations = itmax;
   b.stats.n_converged = nconv;
   if (n_cluster > 0) {
-    std::vector<int32_t> order(b.cl_off[1] + b.cl_cnt[1]);
+    std::vector<int32_t> order(b.cl_off[8] + b.cl_cnt[8]);
     if ((e = cudaMemcpy(order.data(), b.cl_order, sizeof(int32_t) * order.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     int64_t tot = 0;
     int nclusters = 0;
-    for (int k = 0; k < 2; ++k) {
+    int best = 1;
+    for (int k = 1; k <= 8; ++k) {
+      if (P.cl_cnt[k] > P.cl_cnt[best]) best = k;
       for (int i = 0; i < P.cl_cnt[k]; ++i) tot += it[order[b.cl_off[k] + i]];
-      const int capn = pcg_cluster_capacity(c, k ? 8 : 4);
+      const int capn = P.cl_cnt[k] ? pcg_cluster_capacity(c, k) : 0;
       if (P.cl_cnt[k]) nclusters += P.cl_cnt[k] < capn ? P.cl_cnt[k] : capn;
     }
     b.stats.cluster_systems = n_cluster;
-    b.stats.cluster_size = P.cl_cnt[0] >= P.cl_cnt[1] ? 4 : 8;   // the class that solved most systems
+    b.stats.cluster_size = best;   // the class that solved most systems
     b.stats.cluster_count = nclusters;
     b.stats.cluster_iterations = tot;
     cudaEventElapsedTime(&b.stats.cluster_ms, c.ev_c0, c.ev_c1);
     int32_t h_restarts = 0;
-    if ((e = cudaMemcpy(&h_restarts, b.cl_counter + 2, sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(&h_restarts, b.cl_counter, sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     b.stats.refined_systems += h_restarts;
 #ifdef FEA_CLUSTER_PROFILE
     pcg_cluster_profile_dump();

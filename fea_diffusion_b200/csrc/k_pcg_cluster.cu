@@ -112,14 +112,15 @@ template <int CL>
 __device__ __forceinline__ double sum_table(const double* t, int lane) {
   double acc = 0.0;
 #pragma unroll
-  for (int i = 0; i < CL * kClW / 32; ++i) acc += t[lane + 32 * i];
+  for (int i = 0; i < (CL * kClW + 31) / 32; ++i)
+    if (lane + 32 * i < CL * kClW) acc += t[lane + 32 * i];
   return warp_sum(acc);
 }
 
 template <int CL>
 __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
   constexpr int kCl = CL;
-  constexpr int kClass = CL == 4 ? 0 : 1;
+  constexpr int kClass = CL;
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const PcgPtrs& P = *Pp;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
           break;
         }
         restarted = true;                                       // restart from x with the true residual
-        if (rank == 0 && tid == 0) atomicAdd(P.cl_counter + 2, 1);
+        if (rank == 0 && tid == 0) atomicAdd(P.cl_counter, 1);
         status = FEA_SAMPLE_NOT_RUN;
         rz_prev = inf;                                          // beta = 0
         const int c2 = iters + iters / 4 + 100;
@@ -403,7 +404,13 @@ __global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restri
 typedef void (*cluster_fn)(const PcgPtrs*);
 static cluster_fn cluster_kernel(int cl) {
   switch (cl) {
+    case 1: return k_pcg_cluster<1>;
+    case 2: return k_pcg_cluster<2>;
+    case 3: return k_pcg_cluster<3>;
     case 4: return k_pcg_cluster<4>;
+    case 5: return k_pcg_cluster<5>;
+    case 6: return k_pcg_cluster<6>;
+    case 7: return k_pcg_cluster<7>;
     default: return k_pcg_cluster<8>;
   }
 }
@@ -424,7 +431,7 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int
 
 // Co-resident clusters of `cl` CTAs (0 = path unavailable on this device).
 int pcg_cluster_capacity(Ctx& c, int cl) {
-  const int slot = cl == 4 ? 0 : 1;
+  const int slot = cl;
   if (c.cluster_capacity[slot] >= 0) return c.cluster_capacity[slot];
   c.cluster_capacity[slot] = 0;
   if (cudaFuncSetAttribute(cluster_kernel(cl), cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmemBytes) != cudaSuccess) {
@@ -455,22 +462,25 @@ void pcg_cluster_profile_dump() {
 }
 #endif
 
-// Cluster class of a system from its vertex count (an upper bound of its block rows): 0 = 4 CTAs
-// (up to 8192 rows), 1 = 8 CTAs (up to 16384 rows), -1 = too large, streaming kernels.
-int pcg_cluster_class(int64_t n_vertices_of_sample) {
+// Cluster class of a system = CTAs per cluster, from its vertex count (an upper bound of its block
+// rows): the smallest cluster (at least min_cl CTAs) whose CTAs hold the rows, 2048 per CTA.  Small
+// clusters spend fewer SM-cycles in barriers per iteration and pack the GPU better; they stream a
+// larger part of the matrix from L2.  0 = too large for 8 CTAs: streaming kernels.
+int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl) {
   const int64_t pad = (n_vertices_of_sample + kCtaRows - 1) / kCtaRows * kCtaRows;
-  if (pad <= 0) return -1;
-  if (pad / 32 <= 4 * (int64_t)kClSlices) return 0;
-  if (pad / 32 <= 8 * (int64_t)kClSlices) return 1;
-  return -1;
+  if (pad <= 0) return 0;
+  const int64_t rows_per_cta = (int64_t)kClSlices * 32;
+  int64_t cl = (pad + rows_per_cta - 1) / rows_per_cta;
+  if (cl < min_cl) cl = min_cl;
+  return cl <= kClMax ? (int)cl : 0;
 }
 
-cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl) {
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st) {
   const int capn = pcg_cluster_capacity(c, cl);
   if (capn <= 0 || n_systems <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  cluster_config(&cfg, at, cl, n_systems < capn ? n_systems : capn, c.stream);
+  cluster_config(&cfg, at, cl, n_systems < capn ? n_systems : capn, st);
   return cudaLaunchKernelEx(&cfg, cluster_kernel(cl), dP);
 }
 

@@ -30,12 +30,13 @@ struct PcgPtrs {
   int32_t max_iter;
   int32_t two_level;
   // cluster path (k_pcg_cluster.cu): systems small enough to stay on chip.  The cluster size is
-  // a function of the system alone (class 0: 4 CTAs, class 1: 8 CTAs), so that its summation
-  // order -- and therefore every bit of its result -- does not depend on the rest of the batch.
-  const int32_t* cl_order;  // eligible systems: class 0 first, then class 1; largest first in each
-  int32_t cl_off[2];        // first entry of each class in cl_order
-  int32_t cl_cnt[2];        // entries of each class (0 = class not launched)
-  int32_t* cl_counter;      // [2] work-queue heads (device counters, zeroed per solve)
+  // a function of the system alone (class c = clusters of c CTAs, 1..8: the smallest cluster whose
+  // CTAs can hold the system's rows), so that its summation order -- and therefore every bit of
+  // its result -- does not depend on the rest of the batch.
+  const int32_t* cl_order;  // eligible systems grouped by class; largest first in each
+  int32_t cl_off[9];        // first entry of each class in cl_order (index = CTAs per cluster)
+  int32_t cl_cnt[9];        // entries of each class (0 = class not launched)
+  int32_t* cl_counter;      // [1..8] work-queue heads, [0] restarts (device counters, zeroed per solve)
 };
 static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
 

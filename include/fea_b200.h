@@ -108,7 +108,7 @@ typedef struct fea_solve_stats {
   int32_t cluster_count;       /* clusters launched */
   int64_t cluster_iterations;  /* sum of their iteration counts */
   float   cluster_ms;          /* CUDA-event duration of that kernel */
-  int32_t cluster_size;        /* CTAs per cluster (4 or 8) of the class that solved most systems */
+  int32_t cluster_size;        /* CTAs per cluster (1..8) of the class that solved most systems */
   /* residual replacement: systems whose TRUE residual b - K x missed the tolerance after the
    * recursive one had met it, and that were therefore restarted from their current x */
   int32_t refined_systems;
@@ -134,7 +134,8 @@ int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_sto
 /* work submitted to ctx after this call starts only once everything submitted to `other` so far
  * has finished (same device): joins several contexts' streams for one event-timed region */
 int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
-/* integer options: "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
+/* integer options: "cluster_min" smallest thread-block cluster the on-chip path uses (1..8, default
+ * 1; a system gets the smallest cluster whose CTAs hold its rows, 2048 per CTA); "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
  * the streaming kernels; "refine_rounds" restarts from the true residual per solve (default 1;
  * 0 = the true residual is only checked and reported);
  * "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
