@@ -46,9 +46,12 @@ constexpr int kClMax = 8;                   // largest cluster (portable maximum
 #endif
 constexpr int kClT = FEA_CL_THREADS;        // threads per CTA
 constexpr int kClW = kClT / 32;             // warps per CTA
-constexpr int kClRpt = 2048 / kClT;         // block rows per thread (2048 rows per CTA at most)
-constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64)
-constexpr int kClSmemBytes = 227 * 1024;    // dynamic shared memory per CTA
+#ifndef FEA_CL_CTAS_PER_SM
+#define FEA_CL_CTAS_PER_SM 1
+#endif
+constexpr int kClRpt = 4;                   // block rows per thread
+constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
+constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
   double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
@@ -118,7 +121,7 @@ __device__ __forceinline__ double sum_table(const double* t, int lane) {
 }
 
 template <int CL>
-__global__ void __launch_bounds__(kClT, 1) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
+__global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
   constexpr int kCl = CL;
   constexpr int kClass = CL;
   extern __shared__ __align__(128) unsigned char smem[];

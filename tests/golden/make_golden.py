@@ -56,6 +56,12 @@ def main():
     m = read_medit(os.path.join(REF, "applications/composite/test.mesh"))
     out["composite_coors"], out["composite_conn"] = m["coors"], m["conn"]
     meta["composite"] = dict(mesh_sha=sha16(os.path.join(REF, "applications/composite/test.mesh")))
+    # committed dataset images of the composite condition (the real datagen pipeline at image_size 512):
+    # pins for the window sizing, crop and the region / input renders (SURVEY A-16, section 8f rank 4)
+    for png in ("input", "outline", "regions_MaterialRegion0", "regions_MaterialRegion1", "regions_VertexForce0",
+                "regions_VertexConstraint0"):
+        im = np.array(Image.open(os.path.join(REF, "applications/composite", png + ".png")).convert("L"))
+        out["composite_png_" + png] = im
     for t in ("magnitudes", "materials", "ranges"):
         meta["composite_" + t] = open(os.path.join(REF, "applications/composite", t + ".txt")).read()
     # log pins (file:line in SURVEY.md section 8c)

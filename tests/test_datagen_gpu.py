@@ -194,3 +194,26 @@ def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
         assert np.allclose(pd["u"][:, :2], an.displacement[-1], rtol=1e-9, atol=1e-18)
         assert np.allclose(cd["cauchy_strain"], an.cell_strain, rtol=1e-9, atol=1e-18)
     assert np.array_equal(np.array(Image.open(os.path.join(d1, "2", "input.png")).size), [items[0].size] * 2)
+
+
+def test_region_and_input_images_match_the_committed_composite_dataset(tmp_path, golden):
+    """FEAnalysis.save_input_image / save_region_images on the GPU against the reference's own
+    dataset images (applications/composite/*.png): same size, >= 99.4 % pixels bit-equal."""
+    co, cn, kw = cases.composite_args(well_posed=False)
+    kw = dict(force_edges_tags_magnitudes=[], constraints_edges_tags=[], **kw)
+    data_dir, cond_dir = str(tmp_path), str(tmp_path / "c")
+    os.makedirs(cond_dir)
+    write_medit(os.path.join(data_dir, "part.mesh"), co, cn)
+    an = FEAnalysis("part.mesh", data_dir, cond_dir, num_steps=2, strict=False, max_iter=50, **kw)
+    W, b = imaging.plate_window(an.setup.bbox(), 512)
+    an.update_image_size_or_bounds(image_size=W, bounds=b)
+    an.save_input_image(os.path.join(data_dir, "input.png"))
+    an.save_region_images(os.path.join(cond_dir, "regions"))
+    got = {"input": os.path.join(data_dir, "input.png")}
+    for nm in ("MaterialRegion0", "MaterialRegion1", "VertexForce0", "VertexConstraint0"):
+        got["regions_" + nm] = os.path.join(cond_dir, "regions_%s.png" % nm)
+    for name, path_ in got.items():
+        mine = np.array(Image.open(path_))[:, :, 0].astype(int)
+        ref = golden["composite_png_" + name].astype(int)
+        assert mine.shape == ref.shape == (512, 512)
+        assert (mine == ref).mean() >= 0.994 and ((mine < 128) == (ref < 128)).mean() >= 0.996, name
