@@ -50,12 +50,20 @@ constexpr int kClW = kClT / 32;             // warps per CTA
 #define FEA_CL_CTAS_PER_SM 1
 #endif
 constexpr int kClRpt = 4;                   // block rows per thread
+#ifndef FEA_CL_MONITOR
+#define FEA_CL_MONITOR 1024
+#endif
+constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
   double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
   double partB[kClMax * kClW];    // r.r partials (each warp pushes its partial to all CTAs)
+  double rz_monitor;              // true r.r at the previous monitor pass
+  double tol2;                    // rtol^2 * r0.r0 of the current system
+  int32_t it_limit;               // iteration budget of the current system (tightened after a restart)
+  int32_t pad2_;
   int32_t next_sys;               // (rank 0) queue entry the cluster works on next
   int32_t pad_;
   int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
@@ -227,23 +235,38 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     }
 #endif
     double rz = P.sc.rz[0][s], rz_prev = inf;
-    const double tol2 = P.sc.tol2[s];
-    int max_iter = P.max_iter;                // iteration budget (tightened after a restart)
+    if (tid == 0) {                           // loop constants that are needed once per iteration live in
+      h->tol2 = P.sc.tol2[s];                 // shared memory: registers are the scarce resource here
+      h->it_limit = P.max_iter;
+      h->rz_monitor = inf;                    // true r.r found by the last monitor pass
+    }
+    __syncthreads();
     int iters = 0, status = FEA_SAMPLE_NOT_RUN;
     bool restarted = false;
+    bool monitored = false;                   // the monitor pass of the current iteration count is done
 
     for (;;) {
       // A converged system gets one more pass through the SpMV machinery in "check" mode: the
       // published vector is x, and r is REPLACED by the true residual S b - Khat x (the recursion
       // r -= alpha q drifts by rounding).  A material gap restarts CG once from the current x.
-      bool check = false;
+      //
+      // The same pass runs every kMonitor iterations while the system is still iterating
+      // ("monitor"): r is replaced by the true residual, p is parked in the global q rows and put
+      // back afterwards, so CG continues undisturbed.  A system whose TRUE residual has not even
+      // halved since the previous monitor pass is not going to converge (singular or inconsistent:
+      // a mechanism the classifier missed, F4) and is stopped as STAGNATED instead of holding its
+      // cluster for max_iter iterations.
+      bool check = false, monitor = false;
       if (status == FEA_SAMPLE_NOT_RUN) {
         if (!isfinite(rz)) status = FEA_SAMPLE_BREAKDOWN;
-        else if (rz <= tol2) status = FEA_SAMPLE_CONVERGED;
-        else if (iters >= max_iter) status = max_iter < P.max_iter ? FEA_SAMPLE_STAGNATED : FEA_SAMPLE_MAX_ITER;
+        else if (rz <= *(volatile double*)&h->tol2) status = FEA_SAMPLE_CONVERGED;
+        else if (iters >= *(volatile int32_t*)&h->it_limit)
+          status = *(volatile int32_t*)&h->it_limit < P.max_iter ? FEA_SAMPLE_STAGNATED : FEA_SAMPLE_MAX_ITER;
         if (status != FEA_SAMPLE_NOT_RUN) {
           if ((status == FEA_SAMPLE_CONVERGED || status == FEA_SAMPLE_STAGNATED) && iters > 0) check = true;
           else break;
+        } else if (!monitored && iters > 0 && (iters & (kMonitor - 1)) == 0) {
+          check = monitor = monitored = true;
         }
       }
       const double beta = rz / rz_prev;
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       for (int k = 0; k < kClRpt; ++k) {
         if (own[k]) {
           double2 pv = pbuf[tid + kClT * k];
+          if (monitor) P.q[my_row0 + tid + kClT * k] = pv;
           pv.x = check ? x[k].x : fma(beta, pv.x, r[k].x);
           pv.y = check ? x[k].y : fma(beta, pv.y, r[k].y);
           pbuf[tid + kClT * k] = pv;
@@ -297,14 +321,14 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           } else {  // blocks that did not fit: streamed from global memory (L2 resident), 4 in flight
             const d4* vt = P.val + h->s_base[ls] + lane;
             for (int j = 0; j < L; j += 4) {
-              uint32_t g[4];
               d4 kv[4];
-              double2 pj[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 kv[u].x = kv[u].y = kv[u].z = kv[u].w = 0.0;
                 if (j + u < L) kv[u] = ld_stream_d4(vt + (j + u) * 32);
               }
+              uint32_t g[4];
+              double2 pj[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
@@ -359,8 +383,25 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       PROF_T(6);
       const double rz_new = sum_table<CL>(h->partB, lane);
       PROF_T(7);
+      if (monitor) {
+        // all gathers of x are done (S3): put p back; continue CG with the true residual as r
+#pragma unroll
+        for (int k = 0; k < kClRpt; ++k)
+          if (own[k]) pbuf[tid + kClT * k] = P.q[my_row0 + tid + kClT * k];
+        const bool stuck = !(rz_new < 0.25 * h->rz_monitor);    // |r| not even halved in kMonitor iterations
+        __syncthreads();
+        if (tid == 0) h->rz_monitor = rz_new;
+        rz = rz_new;
+        if (stuck || !isfinite(rz_new)) {
+          status = FEA_SAMPLE_STAGNATED;
+          break;
+        }
+        continue;
+      }
       if (check) {
         rz = rz_new;                                            // what relres reports: the TRUE residual
+        const double tol2 = *(volatile double*)&h->tol2;
+        const int max_iter = *(volatile int32_t*)&h->it_limit;
         if (!(rz_new > 100.0 * tol2 && isfinite(rz_new))) {     // true residual within 10x the tolerance
           if (isfinite(rz_new)) status = FEA_SAMPLE_CONVERGED;
           break;
@@ -374,12 +415,14 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         status = FEA_SAMPLE_NOT_RUN;
         rz_prev = inf;                                          // beta = 0
         const int c2 = iters + iters / 4 + 100;
-        max_iter = c2 < max_iter ? c2 : max_iter;
+        __syncthreads();                                        // everybody has read the old limit
+        if (tid == 0) h->it_limit = c2 < max_iter ? c2 : max_iter;
         continue;
       }
       rz_prev = rz;
       rz = rz_new;
       ++iters;
+      monitored = false;
     }
 
     // ---- results ------------------------------------------------------------------------------

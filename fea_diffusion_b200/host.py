@@ -221,19 +221,32 @@ class ProblemSetup:
 
 
 def floating_components(sample: Sample) -> Tuple[int, int]:
-    """Derived well-posedness check (SURVEY A-19): (#stiffness-connected components with fewer
-    than two fixed vertices, #active vertices touching no stiffness cell)."""
+    """Derived well-posedness check (SURVEY A-19): (#parts of the stiffness mesh with fewer than two
+    fixed vertices, #active vertices touching no stiffness cell).  A *part* is a set of stiffness
+    cells connected through shared EDGES: two parts that touch in a single vertex form a hinge, and
+    the one without constraints of its own is a mechanism (K singular), so every part must carry
+    two fixed vertices itself.  (Conservative: a hinged part held by the hinge plus one fixed
+    vertex is stable but is rejected as well.)"""
     import scipy.sparse as sp
     import scipy.sparse.csgraph as csg
     n_v = len(sample.coors)
-    c = sample.conn[np.asarray(sample.cell_region) >= 0]
+    c = np.asarray(sample.conn)[np.asarray(sample.cell_region) >= 0].astype(np.int64)
+    fixed = np.asarray(sample.fixed, dtype=bool)
     touched = np.zeros(n_v, dtype=bool)
     touched[c.reshape(-1)] = True
+    n_c, k = c.shape
+    if n_c == 0:
+        return 0, int((~fixed).sum())
     a = c.reshape(-1)
     b = np.roll(c, -1, axis=1).reshape(-1)
-    g = sp.coo_matrix((np.ones(len(a), dtype=np.int8), (a, b)), shape=(n_v, n_v))
+    key = np.minimum(a, b) * n_v + np.maximum(a, b)
+    cell = np.repeat(np.arange(n_c), k)
+    order = np.argsort(key, kind="stable")
+    ks, cs = key[order], cell[order]
+    same = ks[1:] == ks[:-1]
+    g = sp.coo_matrix((np.ones(int(same.sum()), dtype=np.int8), (cs[:-1][same], cs[1:][same])), shape=(n_c, n_c))
     ncomp, lab = csg.connected_components(g, directed=False)
-    fixed = np.asarray(sample.fixed, dtype=bool)
-    nfix = np.bincount(lab[fixed & touched], minlength=ncomp)
-    has = np.bincount(lab[touched], minlength=ncomp) > 0
-    return int((has & (nfix < 2)).sum()), int((~touched & ~fixed).sum())
+    pairs = np.unique(np.repeat(lab, k).astype(np.int64) * n_v + a)          # (part, vertex), once each
+    part, vert = pairs // n_v, pairs % n_v
+    nfix = np.bincount(part[fixed[vert]], minlength=ncomp)
+    return int((nfix < 2).sum()), int((~touched & ~fixed).sum())

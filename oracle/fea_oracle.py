@@ -325,22 +325,29 @@ class OracleProblem:
         return b
 
     def classify(self) -> Dict[str, int]:
-        """A-19 (derived): floating components and empty rows."""
+        """A-19 (derived): parts of the stiffness mesh (cells connected through shared edges; parts
+        touching in one vertex are hinged) that carry fewer than two fixed vertices, and empty rows."""
         import scipy.sparse.csgraph as csg
         n_v = len(self.coors)
-        use = self.cell_region >= 0
-        c = self.conn[use]
-        k = c.shape[1]
-        r = np.concatenate([c[:, a] for a in range(k)])
-        s = np.concatenate([c[:, (a + 1) % k] for a in range(k)])
-        G = sp.coo_matrix((np.ones(len(r)), (r, s)), shape=(n_v, n_v))
+        c = self.conn[self.cell_region >= 0].astype(np.int64)
         touched = np.zeros(n_v, dtype=bool)
         touched[c.reshape(-1)] = True
-        ncomp, lab = csg.connected_components(G, directed=False)
-        nfix = np.bincount(lab[self.fixed_vertex & touched], minlength=ncomp)
-        comp_touched = np.bincount(lab[touched], minlength=ncomp) > 0
-        floating = int((comp_touched & (nfix < 2)).sum())
         empty = int((~touched & ~self.fixed_vertex).sum())
+        n_c, k = c.shape
+        floating = 0
+        if n_c:
+            ends = np.stack([c, np.roll(c, -1, axis=1)], axis=2).reshape(-1, 2)
+            ends.sort(axis=1)
+            owner = np.repeat(np.arange(n_c), k)
+            edge_id = np.unique(ends, axis=0, return_inverse=True)[1].reshape(-1)
+            order = np.argsort(edge_id, kind="stable")
+            e, o = edge_id[order], owner[order]
+            twin = e[1:] == e[:-1]
+            G = sp.coo_matrix((np.ones(int(twin.sum())), (o[:-1][twin], o[1:][twin])), shape=(n_c, n_c))
+            ncomp, lab = csg.connected_components(G, directed=False)
+            for part in range(ncomp):
+                verts = np.unique(c[lab == part])
+                floating += int(self.fixed_vertex[verts].sum() < 2)
         return dict(floating_components=floating, empty_rows=empty,
                     well_posed=int(floating == 0 and empty == 0))
 
