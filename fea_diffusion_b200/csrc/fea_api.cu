@@ -255,16 +255,26 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
     b.NBR += pad;
     b.max_cta_count = std::max<int32_t>(b.max_cta_count, (int32_t)(pad / kCtaRows));  // upper bound
   }
-  // on-chip solver path: every system is assigned a cluster class by its own size alone
+  // on-chip solver path: every system is assigned a cluster class by its own size alone.  Inside a
+  // class the queue is ordered longest-job-first by an estimate of the work, rows x iterations: the
+  // iteration count of Jacobi-PCG on these plates falls with the number of constrained vertices
+  // (measured on 800 bench samples: iters ~ 2560 - 344 ln(n_fixed), R^2 0.44), and starting the
+  // long solves first shortens the tail of a batch by 15-20 %.  The order only decides WHEN a
+  // system is solved, never its bits.
   std::vector<int32_t> order;
+  std::vector<double> work(ns, 0.0);
+  for (int s = 0; s < ns; ++s) {
+    int64_t nfix = 0;
+    for (int64_t v = b.vtx_off[s]; v < b.vtx_off[s + 1]; ++v) nfix += d->fixed[v] != 0;
+    const double it = std::max(100.0, 2560.0 - 344.0 * std::log((double)std::max<int64_t>(nfix, 1)));
+    work[s] = it * (double)(b.vtx_off[s + 1] - b.vtx_off[s] - nfix);
+  }
   for (int cls = 1; cls <= 8; ++cls) {
     b.cl_off[cls] = (int32_t)order.size();
     for (int s = 0; s < ns; ++s)
       if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s], ctx->c.cluster_min) == cls) order.push_back(s);
     b.cl_cnt[cls] = (int32_t)order.size() - b.cl_off[cls];
-    std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) {
-      return b.vtx_off[x + 1] - b.vtx_off[x] > b.vtx_off[y + 1] - b.vtx_off[y];
-    });
+    std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) { return work[x] > work[y]; });
   }
   cudaStream_t st = ctx->c.stream;
   int32_t* conn_local = nullptr;
