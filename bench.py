@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--plates", type=int, default=100)
@@ -187,7 +187,12 @@ def run_b200(a):
         import torch.distributed as dist_
         dist = dist_
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL is registered for CUDA tensors, gloo for CPU tensors.  The data path has no collective;
+        # the barrier and the max-over-ranks of the timings are host scalars and go over gloo unless
+        # FEA_BENCH_NCCL=1 (an initialised NCCL communicator was measured to slow the persistent
+        # cluster kernels by ~8 %, so it is only created when asked for)
+        dist.init_process_group("cpu:gloo,cuda:nccl")
+    use_nccl = os.environ.get("FEA_BENCH_NCCL", "0") == "1"
     import __graft_entry__ as ge
     ge.build()
     from fea_diffusion_b200 import Context, pack
@@ -214,10 +219,15 @@ def run_b200(a):
         ctx.synchronize()
         torch.cuda.synchronize()
         if dist is not None:
-            dist.barrier()
+            if use_nccl:
+                dist.barrier(device_ids=[local])
+                torch.cuda.synchronize()   # the NCCL barrier kernel spins on SMs until the peers arrive: wait it out
+            else:
+                t = torch.zeros(1)
+                dist.all_reduce(t)         # gloo: a host-side barrier
 
     def max_over_ranks(x):
-        return reduce_scalar(x, "max", device="cuda" if dist is not None else None)
+        return reduce_scalar(x, "max", device="cuda" if (dist is not None and use_nccl) else None)
 
     def device_step(batch):
         batch.assemble().solve(a.rtol, a.max_iter).rasterize(size, affine, t1)
@@ -257,6 +267,7 @@ def run_b200(a):
     # stream + one host thread each) so that copies, host polls and the low-occupancy tail of one
     # batch overlap the bulk of another (fea_diffusion_b200.pipeline.Pipeline) ---------------------
     from fea_diffusion_b200.pipeline import Pipeline
+    a.streams = max(1, min(a.streams, a.steps // 2))   # at least two steps per stream, or there is nothing to overlap
     pipe = Pipeline(local, a.streams, staggered_priorities=False, first=ctx)
     outs = [BatchResult(u=c.pinned_empty((packed.n_vertices, 2), np.float64), ranges=c.pinned_empty((n, 4), np.float64),
                         iters=c.pinned_empty((n,), np.int32), relres=c.pinned_empty((n,), np.float64),
