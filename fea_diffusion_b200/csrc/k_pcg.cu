@@ -29,7 +29,6 @@
 // cost one flag read per CTA.
 #include <cstdio>
 #include <cstdlib>
-#include <cstring>
 
 #include "fea_internal.cuh"
 #include "pcg_params.cuh"
@@ -491,9 +490,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     cudaEventRecord(c.ev_fork, st);
     bool used[3] = {false, false, false};
     int slot = 0;
-    static const int asc = getenv("FEA_CL_ORDER") && !strcmp(getenv("FEA_CL_ORDER"), "asc");
-    for (int kk = 8; kk >= 1; --kk) {
-      const int k = asc ? 9 - kk : kk;
+    for (int k = 8; k >= 1; --k) {
       if (!P.cl_cnt[k]) continue;
       cudaStream_t ks = st;
       if (slot > 0 && c.aux[(slot - 1) % 3]) {
