@@ -535,6 +535,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     }
     int n_active = ncta;  // stale upper bound of the work-list length
     const int k_end = k + max_chunks;
+    const int k_first = k;  // polls of earlier rounds say "everything finished": never read them
     for (; k < k_end; ++k) {
       const int g = grid_class(n_active, ncta);
       cudaGraphExec_t exec = nullptr;
@@ -559,7 +560,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       cudaMemcpyAsync(hf, b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(hf + 1, &dP->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(c.ev_poll[k & 1], st);
-      if (k >= 1) {
+      if (k > k_first) {
         if ((e = cudaEventSynchronize(c.ev_poll[(k - 1) & 1])) != cudaSuccess) return e;
         const int32_t* hp = c.h_flag + 2 * ((k - 1) & 1);
         done_after.push_back(hp[0]);

@@ -260,3 +260,38 @@ def test_one_call_host_path(ctx, built):
     assert r.images.shape == (1, 2, size, size) and (r.images != 255).any()
     assert r.stats["kernel_launches"] > 0
     assert (r.stats["cluster_ms"] > 0 and r.stats["cluster_systems"] == 1) if ctx.path == "onchip" else r.stats["spmv_ms_avg"] > 0
+
+
+def hinged_plates():
+    """Two triangulated squares that touch in ONE vertex; the left one is clamped, the right one
+    only hangs on the hinge and carries a load: a mechanism (rotation about the hinge), K singular
+    and the load not in its range.  Vertex-connected, so a component count by vertices misses it."""
+    n = 12
+    xs, ys = np.meshgrid(np.linspace(0, 1, n + 1), np.linspace(0, 1, n + 1))
+    sq = np.stack([xs.ravel(), ys.ravel()], 1)
+    idx = lambda i, j: j * (n + 1) + i
+    tri = np.array([[idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)] for j in range(n) for i in range(n)] +
+                   [[idx(i, j), idx(i + 1, j + 1), idx(i, j + 1)] for j in range(n) for i in range(n)], dtype=np.int32)
+    right = sq + [1.0, 1.0]                      # shares only the corner (1, 1)
+    co = np.concatenate([sq, right[1:]])         # right[0] == sq[idx(n, n)]
+    remap = np.concatenate([[idx(n, n)], len(sq) + np.arange(len(right) - 1)])
+    cn = np.concatenate([tri, remap[tri]]).astype(np.int32)
+    fixed = np.zeros(len(co), bool)
+    fixed[[idx(0, j) for j in range(n + 1)]] = True
+    rhs = np.zeros((len(co), 2))
+    rhs[len(co) - 1] = (0.0, -100.0)             # far corner of the hanging square
+    D = np.array([[[1.35, 0.58, 0], [0.58, 1.35, 0], [0, 0, 0.38]]]) * 2e5
+    return Sample(co, cn, np.zeros(len(cn), np.int8), D, fixed, rhs)
+
+
+def test_mechanism_is_stopped_early_not_at_max_iter(ctx):
+    from fea_diffusion_b200.host import floating_components
+    smp = hinged_plates()
+    assert floating_components(smp) == (1, 0)          # the hinged part has no constraint of its own
+    good, _ = cases.cantilever()
+    with ctx.create_batch(pack([smp, good.sample])) as b:
+        r = b.assemble().solve(1e-10, 200000).download()
+    assert r.status[1] == SAMPLE_CONVERGED
+    assert r.status[0] in (SAMPLE_STAGNATED, SAMPLE_BREAKDOWN)
+    if ctx.path == "onchip":
+        assert r.iters[0] <= 8192                      # true-residual monitor, not the iteration cap
