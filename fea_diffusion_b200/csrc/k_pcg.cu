@@ -136,18 +136,10 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
 
 typedef void (*spmv_fn)(const PcgPtrs*, int);
 static spmv_fn pick_spmv(int variant) {
-  switch (variant) {  // FEA_SPMV_VARIANT = 100 * U + MINB  (tuning knob)
-    case 108: return k_pcg_spmv<1, 8>;
+  switch (variant) {  // "spmv_variant" option = 100 * U + MINB (tuning knob; measured on B200: 116 best)
     case 112: return k_pcg_spmv<1, 12>;
-    case 116: return k_pcg_spmv<1, 16>;
-    case 208: return k_pcg_spmv<2, 8>;
-    case 210: return k_pcg_spmv<2, 10>;
-    case 212: return k_pcg_spmv<2, 12>;
     case 216: return k_pcg_spmv<2, 16>;
-    case 308: return k_pcg_spmv<3, 8>;
-    case 310: return k_pcg_spmv<3, 10>;
-    case 408: return k_pcg_spmv<4, 8>;
-    case 406: return k_pcg_spmv<4, 6>;
+    case 210: return k_pcg_spmv<2, 10>;
     default: return k_pcg_spmv<1, 16>;
   }
 }

@@ -14,8 +14,9 @@ iters = int(sys.argv[3]) if len(sys.argv) > 3 else 640
 items, _ = build_workload(plates, 4, 64)
 samples = [it.setup.sample for it in items]
 for v in variants:
-    os.environ["FEA_SPMV_VARIANT"] = str(v)
     ctx = Context(0)
+    ctx.set_option("pcg_path", 1)       # the streaming kernels (the on-chip path has no SpMV launch)
+    ctx.set_option("spmv_variant", v)
     packed = pack(samples)
     with ctx.create_batch(packed) as b:
         b.assemble()
