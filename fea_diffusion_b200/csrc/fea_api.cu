@@ -391,6 +391,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.sc.done, b.ns));
   CK(ctx, dalloc(b, &b.sc.iters, b.ns));
   CK(ctx, dalloc(b, &b.sc.cap, b.ns));
+  CK(ctx, dalloc(b, &b.sc.rz_mon, b.ns));
   CK(ctx, dalloc(b, &b.sc.status, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumA, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumB, b.ns));

@@ -54,6 +54,7 @@ struct SysScalars {
   int32_t* done;     // 0 = iterating, 1 = finished
   int32_t* iters;
   int32_t* cap;      // iteration budget of the current (re)start; < max_iter only after a reopen
+  double* rz_mon;    // true r.r at the previous monitor pass (streaming path)
   int32_t* status;
   double* psumA;     // per-system sums of the CTA partials (two-level mode, huge systems only)
   double* psumB;

@@ -190,17 +190,26 @@ __global__ void __launch_bounds__(kT) k_pcg_update(const PcgPtrs* __restrict__ P
 // k_pcg_refine_scalars then either confirms convergence (rz_last = true r.r, which is what relres
 // reports) or, when the true residual is more than 10x the tolerance, reopens the system: CG
 // restarts from the current x with the true residual.
+//
+// monitor = 1: the same pass for systems that are still iterating, every kMonitorChunks chunks: r
+// is replaced by the true residual, p is kept, and a system whose true residual has not even halved
+// since the previous pass is stopped as STAGNATED (singular / inconsistent: it would iterate to
+// max_iter otherwise).
 __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restrict__ Pp,
                                                           const int32_t* __restrict__ vertex_of_row,
                                                           const double* __restrict__ rhs,
-                                                          const double* __restrict__ dscale) {
+                                                          const double* __restrict__ dscale, int monitor) {
   __shared__ double sm[kT / 32];
   const PcgPtrs& P = *Pp;
   const int cta = blockIdx.x;
   const int s = P.sys_of_cta[cta];
   if (s < 0) return;
   const int st = P.sc.status[s];
-  if ((st != FEA_SAMPLE_CONVERGED && st != FEA_SAMPLE_STAGNATED) || P.sc.iters[s] == 0 || P.sc.cap[s] < 0) return;
+  if (monitor) {
+    if (P.sc.done[s]) return;
+  } else if ((st != FEA_SAMPLE_CONVERGED && st != FEA_SAMPLE_STAGNATED) || P.sc.iters[s] == 0 || P.sc.cap[s] < 0) {
+    return;
+  }
   const int64_t row = (int64_t)cta * kT + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int64_t slice = row >> 5;
@@ -224,6 +233,8 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
   const int v = vertex_of_row[row];
   d4 rec;
   rec.x = rec.y = rec.z = rec.w = 0.0;
+  if (monitor) rec = P.rp[row];   // keep p
+  rec.x = rec.y = 0.0;
   if (v >= 0) {
     rec.x = dscale[2 * row] * rhs[2 * (int64_t)v] - a0;
     rec.y = dscale[2 * row + 1] * rhs[2 * (int64_t)v + 1] - a1;
@@ -234,10 +245,25 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
 }
 
 // one warp per system; reopened systems restart CG (beta = 0) from their current x
-__global__ void k_pcg_refine_scalars(const PcgPtrs* __restrict__ Pp, int32_t* __restrict__ n_reopened, int allow_reopen) {
+__global__ void k_pcg_refine_scalars(const PcgPtrs* __restrict__ Pp, int32_t* __restrict__ n_reopened, int allow_reopen,
+                                     int monitor) {
   const PcgPtrs& P = *Pp;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= P.ns) return;
+  if (monitor) {
+    if (P.sc.done[s]) return;
+    const double total = sum_partials(P.partB + P.cta_first[s], P.cta_count[s]);
+    if ((threadIdx.x & 31) != 0) return;
+    P.sc.psumB[s] = total;
+    if (!(total < 0.25 * P.sc.rz_mon[s]) || !isfinite(total)) {
+      P.sc.status[s] = FEA_SAMPLE_STAGNATED;
+      P.sc.done[s] = 1;
+      P.rz_last[s] = total;
+      atomicAdd(P.sc.n_done, 1);
+    }
+    P.sc.rz_mon[s] = total;
+    return;
+  }
   const int st = P.sc.status[s];
   if ((st != FEA_SAMPLE_CONVERGED && st != FEA_SAMPLE_STAGNATED) || P.sc.iters[s] == 0 || P.sc.cap[s] < 0) return;
   const double total = sum_partials(P.partB + P.cta_first[s], P.cta_count[s]);
@@ -363,6 +389,7 @@ __global__ void k_pcg_init_scalars(const PcgPtrs* __restrict__ Pp, const int32_t
   P.sc.psumB[s] = total;
   P.sc.iters[s] = 0;
   P.sc.cap[s] = P.max_iter;
+  P.sc.rz_mon[s] = __longlong_as_double(0x7ff0000000000000LL);
   int st = FEA_SAMPLE_NOT_RUN, dn = 0;
   if (empty[s]) { st = FEA_SAMPLE_EMPTY_ROW; dn = 1; }
   else if (!(total > 0.0)) { st = isfinite(total) ? FEA_SAMPLE_CONVERGED : FEA_SAMPLE_BREAKDOWN; dn = 1; }
@@ -513,8 +540,8 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       // residual replacement: check converged systems against their true residual, reopen failures
       int32_t* d_reopened = b.cl_counter + 9;
       cudaMemsetAsync(d_reopened, 0, sizeof(int32_t), st);
-      k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
-      k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened, round <= c.refine_rounds ? 1 : 0);
+      k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, 0);
+      k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened, round <= c.refine_rounds ? 1 : 0, 0);
       k_compact_active<<<1, 1024, 0, st>>>(dP);
       launches += 3;
       int32_t h_reopened = 0;
@@ -528,6 +555,9 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     int n_active = ncta;  // stale upper bound of the work-list length
     const int k_end = k + max_chunks;
     const int k_first = k;  // polls of earlier rounds say "everything finished": never read them
+    // monitor interval: 1024 iterations for plate-sized systems, longer for large ones whose
+    // convergence curves have long plateaus (one chunk per 128 rows of the largest system)
+    const int mon_chunks = b.max_cta_count > 32 ? b.max_cta_count : 32;
     for (; k < k_end; ++k) {
       const int g = grid_class(n_active, ncta);
       cudaGraphExec_t exec = nullptr;
@@ -548,6 +578,11 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
         k_compact_active<<<1, 1024, 0, st>>>(dP);
       }
       launches += (int64_t)per_iter * kChunk + 1;
+      if ((k - k_first + 1) % mon_chunks == 0) {   // periodic true-residual monitor (see k_pcg_true_residual)
+        k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, 1);
+        k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, nullptr, 0, 1);
+        launches += 2;
+      }
       int32_t* hf = c.h_flag + 2 * (k & 1);
       cudaMemcpyAsync(hf, b.sc.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(hf + 1, &dP->n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st);

@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       // published vector is x, and r is REPLACED by the true residual S b - Khat x (the recursion
       // r -= alpha q drifts by rounding).  A material gap restarts CG once from the current x.
       //
-      // The same pass runs every kMonitor iterations while the system is still iterating
+      // The same pass runs every kMonitor iterations (2 kMonitor for the larger systems of the
+      // 5..8-CTA classes, whose convergence curves have longer plateaus) while the system is iterating
       // ("monitor"): r is replaced by the true residual, p is parked in the global q rows and put
       // back afterwards, so CG continues undisturbed.  A system whose TRUE residual has not even
       // halved since the previous monitor pass is not going to converge (singular or inconsistent:
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         if (status != FEA_SAMPLE_NOT_RUN) {
           if ((status == FEA_SAMPLE_CONVERGED || status == FEA_SAMPLE_STAGNATED) && iters > 0) check = true;
           else break;
-        } else if (!monitored && iters > 0 && (iters & (kMonitor - 1)) == 0) {
+        } else if (!monitored && iters > 0 && (iters & ((CL > 4 ? 2 * kMonitor : kMonitor) - 1)) == 0) {
           check = monitor = monitored = true;
         }
       }
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k)
           if (own[k]) pbuf[tid + kClT * k] = P.q[my_row0 + tid + kClT * k];
-        const bool stuck = !(rz_new < 0.25 * h->rz_monitor);    // |r| not even halved in kMonitor iterations
+        const bool stuck = !(rz_new < 0.25 * h->rz_monitor);    // |r| not even halved in the interval
         __syncthreads();
         if (tid == 0) h->rz_monitor = rz_new;
         rz = rz_new;

@@ -293,5 +293,4 @@ def test_mechanism_is_stopped_early_not_at_max_iter(ctx):
         r = b.assemble().solve(1e-10, 200000).download()
     assert r.status[1] == SAMPLE_CONVERGED
     assert r.status[0] in (SAMPLE_STAGNATED, SAMPLE_BREAKDOWN)
-    if ctx.path == "onchip":
-        assert r.iters[0] <= 8192                      # true-residual monitor, not the iteration cap
+    assert r.iters[0] <= 8192                          # true-residual monitor, not the iteration cap
