@@ -95,19 +95,19 @@ typedef struct fea_batch_info {
 } fea_batch_info;
 
 typedef struct fea_solve_stats {
-  int32_t iterations;       /* lock-step iterations executed (max over samples) */
+  int32_t iterations;       /* PCG iterations of the slowest sample */
   int32_t n_converged;
   int32_t spmv_launches_timed;
   int32_t update_launches_timed;
   float   spmv_ms_avg;      /* CUDA-event average duration of the SpMV kernel launch */
   float   update_ms_avg;    /* same for the fused vector-update kernel */
-  float   solve_ms;         /* whole PCG loop, CUDA events on the ctx stream */
+  float   solve_ms;         /* whole solve (both paths), CUDA events on the ctx stream */
   int64_t kernel_launches;  /* kernels launched by this solve */
   /* on-chip path (one system per thread-block cluster, matrix in shared memory) */
   int32_t cluster_systems;     /* systems solved by k_pcg_cluster in this solve */
-  int32_t cluster_count;       /* clusters launched */
+  int32_t cluster_count;       /* clusters launched (sum over the per-size kernels) */
   int64_t cluster_iterations;  /* sum of their iteration counts */
-  float   cluster_ms;          /* CUDA-event duration of that kernel */
+  float   cluster_ms;          /* CUDA-event duration of the group of per-size kernels */
   int32_t cluster_size;        /* CTAs per cluster (1..8) of the class that solved most systems */
   /* residual replacement: systems whose TRUE residual b - K x missed the tolerance after the
    * recursive one had met it, and that were therefore restarted from their current x */
@@ -134,11 +134,14 @@ int  fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t slot_start, int32_t slot_sto
 /* work submitted to ctx after this call starts only once everything submitted to `other` so far
  * has finished (same device): joins several contexts' streams for one event-timed region */
 int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
-/* integer options: "cluster_min" smallest thread-block cluster the on-chip path uses (1..8, default
- * 1; a system gets the smallest cluster whose CTAs hold its rows, 2048 per CTA); "pcg_path" 0 = auto (systems that fit stay on chip: k_pcg_cluster), 1 = always
- * the streaming kernels; "refine_rounds" restarts from the true residual per solve (default 1;
- * 0 = the true residual is only checked and reported);
- * "spmv_variant" tuning knob of k_pcg_spmv; "use_graphs" 0/1 */
+/* integer options:
+ *   "pcg_path"      0 = auto (systems of up to 16384 block rows are solved on chip by k_pcg_cluster,
+ *                   larger ones by the streaming kernels), 1 = always the streaming kernels
+ *   "cluster_min"   smallest thread-block cluster the on-chip path uses (1..8, default 1); a system
+ *                   gets the smallest cluster whose CTAs hold its rows, 2048 per CTA
+ *   "refine_rounds" restarts from the true residual per solve (default 1; 0 = the true residual
+ *                   is only checked and reported)
+ *   "spmv_variant"  tuning knob of k_pcg_spmv;  "use_graphs" 0/1 (streaming path) */
 int  fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this context has launched so far (graph nodes included) */
 int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
@@ -150,7 +153,8 @@ int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
  *            matrix graph (sfepy mesh_graph inside problem.solve, :437; A-11),
  *            value assembly with Dirichlet rows/cols dropped (A-10), Jacobi scaling,
  *            load vector (dw_point_load, :338-344).
- * solve    : Jacobi-preconditioned fp64 CG for all samples lock-step; replaces
+ * solve    : Jacobi-preconditioned fp64 CG of every sample (on chip, one sample per thread-block
+ *            cluster, or lock-step streaming kernels for large systems); replaces
  *            Newton + ScipyDirect + SimpleTimeSteppingSolver (:371-375, 425-439):
  *            one solve at t = 1, load steps are t_k multiples of it (F5).
  *            Also produces per-sample (min,max) of both components (ranges.txt, A-17).
@@ -168,7 +172,8 @@ int  fea_batch_destroy(fea_batch* b);
 /* ---- results (host buffers, may be NULL to skip) ------------------------- */
 /* u [n_vertices*2] final-step displacement, zeros at fixed DOFs (A-15), NaN for EMPTY_ROW
  * samples; ranges [n_samples*4] = (min ux, max ux, min uy, max uy) of the final step;
- * iters/status [n_samples]; relres [n_samples] = sqrt(r.z / r0.z0) at exit. */
+ * iters/status [n_samples]; relres [n_samples] = sqrt(r.r / r0.r0) of the TRUE residual
+ * r = S (b - K u) in the Jacobi-scaled norm for converged / stagnated samples. */
 int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
                         double* relres, int32_t* status);
 int  fea_batch_download_images(fea_batch* b, uint8_t* images);
