@@ -38,6 +38,7 @@ struct Ctx {
   int refine_rounds = 1;               // restarts from the true residual per solve (0 = check only)
   int pcg_path = 0;                    // 0 = auto (on-chip cluster kernel where systems fit), 1 = streaming only
   int cluster_capacity[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // co-resident clusters of c CTAs (-1 = not queried)
+  int row_order = 3;                   // solver row order: 0 = input numbering, 1 = Morton, 2 = strips, 3 = auto
   int cluster_min = 1;                 // smallest cluster size used (1..8)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // cluster kernels of different classes run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -85,6 +86,7 @@ struct Batch {
   int32_t* flips = nullptr;      // [ns]
   // equation map
   int32_t* vrank = nullptr;      // [NV] rank among active vertices of the sample, -1 if fixed
+  int32_t* prank = nullptr;      // [NV] the same in the solver's spatial row order (k_spatial_rank)
   int32_t* n_active = nullptr;   // [ns] active vertices
   int64_t* row_base = nullptr;   // [ns+1] first (padded) block row of each sample
   int64_t NBR = 0;               // allocated block rows (upper bound, multiple of kCtaRows)

@@ -139,6 +139,10 @@ int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
  *                   larger ones by the streaming kernels), 1 = always the streaming kernels
  *   "cluster_min"   smallest thread-block cluster the on-chip path uses (1..8, default 1); a system
  *                   gets the smallest cluster whose CTAs hold its rows, 2048 per CTA
+ *   "row_order"     order of the rows inside the solver: 0 = the input vertex numbering, 1 = Morton
+ *                   code, 2 = strips, 3 = auto (default: keep a numbering that is already local,
+ *                   sort by strips otherwise).  It decides how local the SpMV gathers are, never
+ *                   what is exported (fea_batch_get_csr always follows sfepy's numbering)
  *   "refine_rounds" restarts from the true residual per solve (default 1; 0 = the true residual
  *                   is only checked and reported)
  *   "spmv_variant"  tuning knob of k_pcg_spmv;  "use_graphs" 0/1 (streaming path) */

@@ -114,3 +114,38 @@ def test_linearity_in_the_load(ctx, solved):
         r3 = b.assemble().solve(1e-11, 50000).download()
     u = solved[seed][2].u
     assert np.linalg.norm(r3.u - 3.0 * u) / np.linalg.norm(3.0 * u) <= 1e-9
+
+
+def test_result_does_not_depend_on_the_input_vertex_numbering(ctx):
+    """The solver sorts every sample's rows spatially when the input numbering is not local
+    (row_order auto): a randomly renumbered mesh gives the same displacements (to rounding) as the
+    original, and the exported CSR pattern still follows the numbering it was given (A-9/A-11)."""
+    from fea_diffusion_b200.host import floating_components
+    seed = next(s for s in range(5, 40) if floating_components(ProblemSetup(*random_case(s)[:2], **random_case(s)[2]).sample) == (0, 0))
+    co, tri, kw = random_case(seed)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(co))
+    inv = np.empty(len(co), np.int64)
+    inv[perm] = np.arange(len(co))
+    kw2 = dict(kw)
+    kw2["force_vertex_tags_magnitudes"] = [(int(inv[t - 1]) + 1, m) for t, m in kw["force_vertex_tags_magnitudes"]]
+    kw2["constraints_edges_tags"] = [(int(inv[a - 1]) + 1, int(inv[b - 1]) + 1) for a, b in kw["constraints_edges_tags"]]
+    kw2["material_properties_to_vertices"] = kw["material_properties_to_vertices"]
+    s1 = ProblemSetup(co, tri, **kw)
+    s2 = ProblemSetup(co[perm], inv[tri].astype(np.int32), **kw2)
+    assert np.array_equal(np.asarray(s2.sample.fixed), np.asarray(s1.sample.fixed)[perm])
+    res = {}
+    for order in (0, 1, 2, 3):
+        ctx.set_option("row_order", order)
+        with ctx.create_batch(pack([s1.sample, s2.sample])) as b:
+            r = b.assemble().solve(1e-11, 50000).download()
+            us = b.packed.split_vertices(r.u)
+            K2 = b.csr(1)
+        assert (r.status == SAMPLE_CONVERGED).all()
+        assert np.linalg.norm(us[1] - us[0][perm]) / np.linalg.norm(us[0]) <= 1e-9
+        res[order] = us[0]
+        A2 = OracleProblem(co[perm], inv[tri].astype(np.int32), num_steps=2, **kw2).stiffness()
+        assert np.array_equal(K2.indptr, A2.indptr) and np.array_equal(K2.indices, A2.indices)
+    ctx.set_option("row_order", 3)
+    for order in (1, 2, 3):
+        assert np.linalg.norm(res[order] - res[0]) / np.linalg.norm(res[0]) <= 1e-9
