@@ -91,10 +91,13 @@ __device__ __forceinline__ double2 ld_shared_f64x2(uint32_t addr) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
-// gather of a published p entry: bit 0 of the precomputed address marks an entry of ANOTHER CTA
-// (distributed shared memory, ~20 B/clk per SM); own entries use the plain 128 B/clk path
-__device__ __forceinline__ double2 ld_p(uint32_t g) {
-  return (g & 1u) ? ld_cluster_f64x2(g & ~1u) : ld_shared_f64x2(g);
+// gather of a published p entry from its 16-bit code: bits 0-10 row inside the owning CTA, bits
+// 11-13 rank of that CTA, bit 15 set for an entry of ANOTHER CTA (distributed shared memory,
+// ~20 B/clk per SM); own entries use the plain 128 B/clk path.  Two bytes per block instead of a
+// 4-byte address leave room for ~10 % more matrix blocks in shared memory.
+__device__ __forceinline__ double2 ld_p(uint32_t code, uint32_t pbuf_a) {
+  const uint32_t la = pbuf_a + 16u * (code & 0x7ffu);
+  return (code & 0x8000u) ? ld_cluster_f64x2(mapa_u32(la, (code >> 11) & 7u)) : ld_shared_f64x2(la);
 }
 __device__ __forceinline__ double ld_cluster_f64(uint32_t addr) {
   double v;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     const int cap = kClSmemBytes - mat0;
 
     // ---- slice table + copy of the CTA's matrix slices into shared memory ------------------------
-    // gather addresses (4 B per block) of ALL owned slices are kept on chip; the 32-byte blocks of
+    // gather codes (2 B per block) of ALL owned slices are kept on chip; the 32-byte blocks of
     // as many slices as fit follow them, the rest is streamed from global memory (L2) every iteration
     if (tid < kClSlices) {
       h->s_len[tid] = tid < my_sl ? P.slice_len[(my_row0 >> 5) + tid] : 0;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     if (tid == 0) {
       int ent = 0;
       for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += h->s_len[i] * 32; }
-      int off = (ent * 4 + 127) / 128 * 128;
+      int off = (ent * 2 + 127) / 128 * 128;
       for (int i = 0; i < kClSlices; ++i) {
         const int bytes = h->s_len[i] * 32 * 32;
         if (i < my_sl && off + bytes <= cap) { h->s_off[i] = off; off += bytes; }
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     }
     __syncthreads();
     const uint32_t pbuf_a = smem_u32(pbuf);
-    uint32_t* sa_all = reinterpret_cast<uint32_t*>(smem + mat0);
+    uint16_t* sa_all = reinterpret_cast<uint16_t*>(smem + mat0);
 #pragma unroll
     for (int k = 0; k < kClRpt; ++k) {
       const int ls = warp + kClW * k;        // local slice handled by this warp
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       const int off = h->s_off[ls];
       const int L = h->s_len[ls];
       const int64_t base = h->s_base[ls];
-      uint32_t* sa = sa_all + h->s_aoff[ls];
+      uint16_t* sa = sa_all + h->s_aoff[ls];
       // values per slice: L x 32 top halves (k00,k01) then L x 32 bottom halves (k10,k11)
       // (16-byte lane stride: conflict-free 128-bit shared loads)
       double2* st = reinterpret_cast<double2*>(smem + mat0 + (off < 0 ? 0 : off));
@@ -206,8 +209,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
         const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;   // row inside the system
         const int cr = c / Rc;
-        const uint32_t la = pbuf_a + 16u * (uint32_t)(c - cr * Rc);
-        sa[j * 32 + lane] = cr == rank ? la : (mapa_u32(la, (uint32_t)cr) | 1u);
+        sa[j * 32 + lane] = (uint16_t)((c - cr * Rc) | (cr << 11) | (cr == rank ? 0 : 0x8000));
       }
     }
 
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           a1 = fma(dck, pk.x, pk.y);
           const int L = h->s_len[ls];
           const int off = h->s_off[ls];
-          const uint32_t* sa = sa_all + h->s_aoff[ls] + lane;
-          const uint32_t self = pbuf_a + 16u * (uint32_t)(tid + kClT * k);
+          const uint16_t* sa = sa_all + h->s_aoff[ls] + lane;
+          const uint32_t self = (uint32_t)(tid + kClT * k);
           if (off >= 0) {
             const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
             const double2* sb = st + L * 32;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
               for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u]) : make_double2(0.0, 0.0);
+              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u], pbuf_a) : make_double2(0.0, 0.0);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 if (j + u < L) {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
               for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u]) : make_double2(0.0, 0.0);
+              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u], pbuf_a) : make_double2(0.0, 0.0);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
