@@ -483,8 +483,11 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   PcgPtrs P = make_ptrs(b, max_iter);
   int n_cluster = 0;
   P.cl_cnt[0] = 0;
+  // the gather codes of a CTA's slices (2 B per block, up to 64 slices of 32 rows) must fit beside
+  // the vectors in shared memory: meshes with extreme vertex valences use the streaming kernels
+  const bool codes_fit = (int64_t)b.max_row_blocks * 64 * 32 * 2 <= 160 * 1024;
   for (int k = 1; k <= 8; ++k) {
-    if (c.pcg_path != 0 || (P.cl_cnt[k] && pcg_cluster_capacity(c, k) <= 0)) P.cl_cnt[k] = 0;
+    if (c.pcg_path != 0 || !codes_fit || (P.cl_cnt[k] && pcg_cluster_capacity(c, k) <= 0)) P.cl_cnt[k] = 0;
     n_cluster += P.cl_cnt[k];
   }
   const bool two = P.two_level != 0;
