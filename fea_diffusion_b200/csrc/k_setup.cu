@@ -387,11 +387,8 @@ cudaError_t launch_setup(Batch& b, const int8_t* d_creg_local, const int32_t* d_
   if (ncta) k_cta_sys<<<(ncta + T - 1) / T, T, 0, st>>>(b.row_base, b.ns, ncta, b.sys_of_cta);
   const int32_t* rank_for_rows = b.vrank;
   if (b.ctx->row_order != 0 && b.prank) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_spatial_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * 8);
-      attr_set = true;
-    }
+    // (function attributes are per device: set it on every call, it costs microseconds)
+    cudaFuncSetAttribute(k_spatial_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * 8);
     int64_t nvmax = 0;
     for (int s = 0; s < b.ns; ++s) nvmax = std::max<int64_t>(nvmax, b.vtx_off[s + 1] - b.vtx_off[s]);
     int n2 = 1;
