@@ -316,7 +316,9 @@ def run_b200(a):
                               "of a thread-block cluster and its CG vectors stay in registers, so achieved algorithmic GB/s "
                               "exceeds the HBM peak by design; HBM-streaming figures of the same iterations are in "
                               "'streaming_path'",
-                    "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"]}
+                    "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"],
+                    "l2_read_peak_gbs": 17900.0, "hbm_read_peak_gbs": 6880.0,
+                    "peaks_note": "L2-resident / HBM-resident read bandwidth measured with tools/l2_bw.cu on a B200 of this pool"}
     else:
         roofline = None
     # the streaming kernels on the same batch (one extra, untimed-region solve): the HBM-bound SpMV
