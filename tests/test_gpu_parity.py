@@ -294,3 +294,28 @@ def test_mechanism_is_stopped_early_not_at_max_iter(ctx):
     assert r.status[1] == SAMPLE_CONVERGED
     assert r.status[0] in (SAMPLE_STAGNATED, SAMPLE_BREAKDOWN)
     assert r.iters[0] <= 8192                          # true-residual monitor, not the iteration cap
+
+
+@pytest.mark.parametrize("nx,ny,cl", [(48, 30, 1), (70, 42, 2), (90, 55, 3), (105, 66, 4), (118, 76, 5),
+                                      (130, 84, 6), (140, 92, 7), (150, 102, 8)])
+def test_every_cluster_size_agrees_with_the_streaming_path(nx, ny, cl):
+    """The on-chip solver picks 1..8 CTAs per cluster from the system size: one Q1 plate per
+    class, solved on chip and by the streaming kernels (which the goldens pin)."""
+    setup, _ = cases.quad_plate(nx, ny)
+    rows = -(-((nx + 1) * (ny + 1)) // 128) * 128
+    assert -(-rows // 2048) == cl
+    out = {}
+    for path in (0, 1):
+        c = Context(0)
+        c.set_option("pcg_path", path)
+        try:
+            with c.create_batch(pack([setup.sample])) as b:
+                r = b.assemble().solve(1e-11, 200000).download()
+                st = b.stats()
+        finally:
+            c.close()
+        assert r.status[0] == SAMPLE_CONVERGED
+        assert (st["cluster_systems"], st["cluster_size"] if path == 0 else cl) == (1 - path, cl)
+        out[path] = r
+    assert rel(out[0].u, out[1].u) <= 1e-9
+    assert abs(int(out[0].iters[0]) - int(out[1].iters[0])) <= max(3, out[1].iters[0] // 200)
