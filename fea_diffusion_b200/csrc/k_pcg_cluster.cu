@@ -3,24 +3,26 @@
 // datagen/fea_analysis.py:371-375, 425-439) for the plate-sized systems of the data-synthesis loop.
 //
 // A default-density plate has 2.5-10 k vertices: its scaled block-SELL matrix is 0.5-2.3 MB and its
-// CG vectors a few hundred KB.  That fits the shared memory + registers of 8 SMs, so a cluster of
-// 8 CTAs x 512 threads keeps ONE system on chip for its whole solve:
+// CG vectors a few hundred KB.  A thread-block cluster of CL CTAs x 512 threads keeps ONE system on
+// chip for its whole solve; CL (1..8) is the smallest cluster whose CTAs hold the system's rows
+// (2048 per CTA), one persistent kernel per CL, launched on concurrent streams (run_pcg):
 //
-//   * every CTA owns a contiguous range of the system's 32-row slices; its slices of the matrix
-//     are copied from HBM to shared memory ONCE (slices that do not fit stay in global memory and
-//     are streamed from L2 every iteration);
-//   * x, r, p of a thread's (up to 4) block rows live in registers for the whole solve;
-//   * the search direction p is published in shared memory and gathered by the neighbours
-//     through distributed shared memory (ld.shared::cluster); the gather addresses are
-//     precomputed when the matrix is loaded;
-//   * dot products: every warp pushes its partial into a table in all 8 CTAs (st.shared::cluster);
+//   * every CTA owns a contiguous range of the system's 32-row slices; the gather codes of all its
+//     slices and the 2x2 blocks of as many slices as fit are copied from HBM to shared memory ONCE,
+//     the blocks of the other slices are streamed from L2 every iteration;
+//   * x, r of a thread's (up to 4) block rows live in registers for the whole solve;
+//   * the search direction p is published in shared memory and gathered by the neighbours --
+//     plain ld.shared inside the CTA, mapa + ld.shared::cluster (distributed shared memory) across;
+//   * dot products: every warp pushes its partial into a table in all CTAs (st.shared::cluster);
 //     after the barrier every warp adds its local copy in the same fixed order -- no atomics,
 //     bitwise reproducible, independent of which cluster or SM runs the system;
-//   * three cluster barriers per iteration (p published, p.q partials, r.r partials).
+//   * three cluster barriers per iteration (p published, p.q partials, r.r partials);
+//   * a converged system is verified against its TRUE residual (and restarted once if the gap is
+//     material); every 1024 iterations the same pass monitors progress and stops mechanisms.
 //
-// Clusters are persistent and pull systems from a queue (largest first), so there is no lock-step
-// and no tail of idle CTAs waiting for the slowest system of a batch.  HBM traffic is one read of
-// the matrix and vectors per SOLVE instead of per iteration.
+// Clusters are persistent and pull systems from a queue (longest job first), so there is no
+// lock-step and no tail of idle CTAs waiting for the slowest system of a batch.  HBM traffic is one
+// read of the matrix and vectors per SOLVE instead of per iteration.
 // Systems too large for a cluster (> 16 384 block rows) keep using the streaming kernels of k_pcg.cu.
 #include <cooperative_groups.h>
 
