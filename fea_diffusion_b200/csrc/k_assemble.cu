@@ -57,11 +57,13 @@ __device__ __forceinline__ void block_of_pair(int v, int w, const int32_t* __res
 #pragma unroll
     for (int bb = 0; bb < NPC; ++bb) {
       if (conn[c * NPC + bb] == w) {
-        const double* K = ke + c * (N * N);
-        k[0] += K[(2 * a) * N + 2 * bb];
-        k[1] += K[(2 * a) * N + 2 * bb + 1];
-        k[2] += K[(2 * a + 1) * N + 2 * bb];
-        k[3] += K[(2 * a + 1) * N + 2 * bb + 1];
+        const double* K = ke + c * (N * N);   // both pairs are 16-byte aligned (even offsets)
+        const double2 top = __ldg(reinterpret_cast<const double2*>(K + (2 * a) * N + 2 * bb));
+        const double2 bot = __ldg(reinterpret_cast<const double2*>(K + (2 * a + 1) * N + 2 * bb));
+        k[0] += top.x;
+        k[1] += top.y;
+        k[2] += bot.x;
+        k[3] += bot.y;
       }
     }
   }

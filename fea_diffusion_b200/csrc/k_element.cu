@@ -60,9 +60,17 @@ __global__ void k_element_p1(int64_t NC, const double* __restrict__ xy, const in
     const double gy[3] = {c0 * inv, c1 * inv, c2 * inv};
     accumulate_btdb<3>(gx, gy, D, 0.5 * fabs(det), K);
   }
-  double* out = ke + c * 36;
+  // 288 B per cell = nine 32-byte sectors: 256-bit stores write whole sectors
+  d4* out = reinterpret_cast<d4*>(ke + c * 36);
 #pragma unroll
-  for (int i = 0; i < 36; ++i) out[i] = K[i];
+  for (int i = 0; i < 9; ++i) {
+    d4 v;
+    v.x = K[4 * i];
+    v.y = K[4 * i + 1];
+    v.z = K[4 * i + 2];
+    v.w = K[4 * i + 3];
+    out[i] = v;
+  }
 }
 
 __global__ void k_element_q1(int64_t NC, const double* __restrict__ xy, const int32_t* __restrict__ conn,
@@ -111,9 +119,16 @@ __global__ void k_element_q1(int64_t NC, const double* __restrict__ xy, const in
       accumulate_btdb<4>(gx, gy, D, 0.25 * fabs(det), K);
     }
   }
-  double* out = ke + c * 64;
+  d4* out = reinterpret_cast<d4*>(ke + c * 64);
 #pragma unroll
-  for (int i = 0; i < 64; ++i) out[i] = K[i];
+  for (int i = 0; i < 16; ++i) {
+    d4 v;
+    v.x = K[4 * i];
+    v.y = K[4 * i + 1];
+    v.z = K[4 * i + 2];
+    v.w = K[4 * i + 3];
+    out[i] = v;
+  }
 }
 
 // Post-process of the reference's calculate_stress_strain hook (datagen/fea_analysis.py:397-416):
