@@ -57,6 +57,12 @@ constexpr int kClRpt = 4;                   // block rows per thread
 #endif
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
+#ifndef FEA_CL_ASYNC_RED
+#define FEA_CL_ASYNC_RED 1                  // dot-product partials by st.async + mbarrier (0: cluster barriers)
+#endif
+#ifndef FEA_CL_S1_MODE
+#define FEA_CL_S1_MODE 0                    // how the published p becomes visible (see publish_sync)
+#endif
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
@@ -68,6 +74,7 @@ struct ClHeader {                 // start of the dynamic shared memory of every
   int32_t pad2_;
   int32_t next_sys;               // (rank 0) queue entry the cluster works on next
   int32_t pad_;
+  uint64_t mbarA, mbarB;          // transaction barriers: all partials of a p.q / r.r phase have landed
   int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
   int32_t s_len[kClSlices];       // blocks per row of the slice
   int32_t s_aoff[kClSlices];      // entry offset of the slice's gather addresses
@@ -116,13 +123,59 @@ __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-// Dot products over the cluster, push model: lane c < 8 of every warp stores the warp's partial
-// into slot [rank][warp] of CTA c's table; after the cluster barrier every warp of every CTA adds
-// the 128 slots of its own copy in the same fixed order, so all of them hold the same bits and no
-// intra-CTA broadcast is needed.
+// Dot products over the cluster, push model: lane c < CL of every warp stores the warp's partial
+// into slot [rank][warp] of CTA c's table; once all CL x 16 partials of a phase have landed every
+// warp of every CTA adds the slots of its own copy in the same fixed order, so all of them hold the
+// same bits and no intra-CTA broadcast is needed.
+//
+// "Landed" is signalled without a cluster barrier: the partial travels as st.async, which adds its
+// 8 bytes to the transaction count of an mbarrier in the DESTINATION CTA; every thread waits on its
+// own CTA's mbarrier (try_wait, acquire at cluster scope).  Compared with barrier.cluster this needs
+// no release fence over the CTA's earlier stores and no cluster-wide rendezvous.  A phase cannot be
+// overtaken: the partials of iteration k+1 are pushed after the S1 barrier of k+1, which every
+// thread reaches only after it has consumed phase k; thread 0 re-arms the barrier (arrive +
+// expect_tx) as soon as it has seen a phase complete -- partials that arrive before that only make
+// the transaction count transiently negative while the pending arrival keeps the phase open.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(mbar), "r"(parity) : "memory");
+}
 template <int CL>
-__device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, int rank, int warp, int lane, double v) {
+__device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, uint32_t mbar_off, int rank, int warp, int lane, double v) {
+#if FEA_CL_ASYNC_RED
+  if (lane < CL) {
+    const uint32_t base = mapa_u32(smem_u32(h), lane);   // the header of CTA `lane`
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(
+                     base + field_off + 8u * (uint32_t)(rank * kClW + warp)),
+                 "d"(v), "r"(base + mbar_off)
+                 : "memory");
+  }
+#else
   if (lane < CL) st_cluster_f64(mapa_u32(smem_u32(h) + field_off + 8u * (uint32_t)(rank * kClW + warp), lane), v);
+#endif
+}
+// all partials of the phase are in this CTA's table (parity = phases of this barrier seen so far, mod 2)
+template <int CL>
+__device__ __forceinline__ void await_partials(cg::cluster_group& cluster, ClHeader* h, uint64_t* mbar, uint32_t parity, int tid) {
+#if FEA_CL_ASYNC_RED
+  mbar_wait(smem_u32(mbar), parity);
+  if (tid == 0) mbar_arm(smem_u32(mbar), 8u * CL * kClW);
+#else
+  cluster.sync();
+#endif
 }
 template <int CL>
 __device__ __forceinline__ double sum_table(const double* t, int lane) {
@@ -131,6 +184,23 @@ __device__ __forceinline__ double sum_table(const double* t, int lane) {
   for (int i = 0; i < (CL * kClW + 31) / 32; ++i)
     if (lane + 32 * i < CL * kClW) acc += t[lane + 32 * i];
   return warp_sum(acc);
+}
+
+// S1: the p entries every thread wrote into its CTA's shared memory become visible to the gathers
+// of the whole cluster.
+__device__ __forceinline__ void publish_sync(cg::cluster_group& cluster, int tid) {
+#if FEA_CL_S1_MODE == 1
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#elif FEA_CL_S1_MODE == 2
+  // one release fence per CTA instead of one per thread: bar.sync orders the CTA's stores before
+  // thread 0's fence (cumulativity), the fence + relaxed arrive form the release pattern
+  __syncthreads();
+  if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+#else
+  cluster.sync();
+#endif
 }
 
 template <int CL>
@@ -145,6 +215,17 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  uint32_t phase = 0;   // bit 0 / bit 1: parity of the p.q / r.r barrier phase that is awaited next
+#if FEA_CL_ASYNC_RED
+  if (tid == 0) {
+    mbar_init(smem_u32(&h->mbarA), 1);
+    mbar_init(smem_u32(&h->mbarB), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arm(smem_u32(&h->mbarA), 8u * CL * kClW);
+    mbar_arm(smem_u32(&h->mbarB), 8u * CL * kClW);
+  }
+  // (the first cluster.sync() of the queue loop below orders the initialisation before any push)
+#endif
 
   for (;;) {
     // ---- next system of the queue (rank 0 pulls, everyone reads it through DSMEM) --------------
@@ -288,7 +369,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
       }
       PROF_T(0);
-      cluster.sync();                                           // S1: every CTA's p is visible
+      publish_sync(cluster, tid);                               // S1: every CTA's p is visible
       PROF_T(1);
       double2 q[kClRpt];
       double part = 0.0;
@@ -353,9 +434,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       }
       if (!check) {
         part = warp_sum(part);
-        push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partA), rank, warp, lane, part);
+        push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partA), (uint32_t)offsetof(ClHeader, mbarA), rank, warp, lane, part);
         PROF_T(2);
-        cluster.sync();                                         // S2: p.q partials visible
+        await_partials<CL>(cluster, h, &h->mbarA, phase & 1u, tid);   // S2: p.q partials visible
+        phase ^= 1u;
         PROF_T(3);
         const double pq = sum_table<CL>(h->partA, lane);
         PROF_T(4);
@@ -384,9 +466,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
       }
       part = warp_sum(part);
-      push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), rank, warp, lane, part);
+      push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), (uint32_t)offsetof(ClHeader, mbarB), rank, warp, lane, part);
       PROF_T(5);
-      cluster.sync();                                           // S3: r.r partials visible
+      await_partials<CL>(cluster, h, &h->mbarB, (phase >> 1) & 1u, tid);   // S3: r.r partials visible
+      phase ^= 2u;
       PROF_T(6);
       const double rz_new = sum_table<CL>(h->partB, lane);
       PROF_T(7);
