@@ -40,6 +40,7 @@ struct Ctx {
   int cluster_capacity[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // co-resident clusters of c CTAs (-1 = not queried)
   int row_order = 3;                   // solver row order: 0 = input numbering, 1 = Morton, 2 = strips, 3 = auto
   int cluster_min = 1;                 // smallest cluster size used (1..8)
+  int cluster_halo_cap = 1 << 30;      // test knob: on-chip systems with a larger per-CTA halo go to the streaming path
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // cluster kernels of different classes run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
@@ -99,7 +100,7 @@ struct Batch {
   int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
   int32_t* cl_order = nullptr;       // [ns] systems of the cluster path: class 0 then class 1
   int32_t cl_off[9] = {}, cl_cnt[9] = {};   // index = CTAs per cluster
-  int32_t* cl_counter = nullptr;     // [16] device work-queue heads [1..8], restart count [0], scratch [9]
+  int32_t* cl_counter = nullptr;     // [16] device work-queue heads [1..8], restart count [0], scratch [9], handed back [10]
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending

@@ -427,6 +427,7 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
     P.cl_cnt[k] = b.cl_cnt[k];
   }
   P.cl_counter = b.cl_counter;
+  P.cl_halo_cap = b.ctx->cluster_halo_cap;
   return P;
 }
 
@@ -553,7 +554,12 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       reopened_total += h_reopened;
       if (h_reopened == 0) break;
     } else if (n_cluster >= b.ns) {
-      break;      // everything was solved AND verified against its true residual on chip
+      // everything was solved AND verified against its true residual on chip -- unless a cluster
+      // handed its system back (halo of a CTA too large for its shared memory)
+      int32_t h_back = 0;
+      if ((e = cudaMemcpyAsync(&h_back, b.cl_counter + 10, sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+      if (h_back == 0) break;
     }
     int n_active = ncta;  // stale upper bound of the work-list length
     const int k_end = k + max_chunks;

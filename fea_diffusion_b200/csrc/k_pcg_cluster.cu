@@ -57,27 +57,30 @@ constexpr int kClRpt = 4;                   // block rows per thread
 #endif
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
-#ifndef FEA_CL_ASYNC_RED
-#define FEA_CL_ASYNC_RED 1                  // dot-product partials by st.async + mbarrier (0: cluster barriers)
-#endif
-#ifndef FEA_CL_S1_MODE
-#define FEA_CL_S1_MODE 0                    // how the published p becomes visible (see publish_sync)
-#endif
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
+constexpr int kClWords = kClMax * kClSlices;   // 32-row slices of the largest system = words of the halo bitmap
+static_assert(kClWords == kClT, "the halo scan handles one bitmap word per thread");
+constexpr int kClTmpBytes = 2 * kClWords * 4 + 128;   // halo bitmap + its prefix sums (set-up only)
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
   double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
   double partB[kClMax * kClW];    // r.r partials (each warp pushes its partial to all CTAs)
   double rz_monitor;              // true r.r at the previous monitor pass
   double tol2;                    // rtol^2 * r0.r0 of the current system
+  uint64_t mbarA, mbarB, mbarP;   // transaction barriers: p.q partials / r.r partials / halo of p have landed
   int32_t it_limit;               // iteration budget of the current system (tightened after a restart)
-  int32_t pad2_;
   int32_t next_sys;               // (rank 0) queue entry the cluster works on next
+  int32_t n_send;                 // entries of this CTA's send list
+  int32_t off_pbuf, mat0;         // byte offsets of the p buffer and of the matrix area
   int32_t pad_;
-  uint64_t mbarA, mbarB;          // transaction barriers: all partials of a p.q / r.r phase have landed
+  int32_t send_from[kClMax];      // (owner side) rows of this CTA that CTA c gathers
+  int32_t seg_off[kClMax];        // (consumer side) first entry of this CTA's segment in owner o's send list
+  int32_t fit[kClMax];            // the layout of CTA c fits into its shared memory
+  int32_t wsum[kClW];             // block-scan scratch
+  int32_t s_halo[kClSlices];      // the slice gathers rows of other CTAs (its warp waits for the halo first)
   int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
   int32_t s_len[kClSlices];       // blocks per row of the slice
-  int32_t s_aoff[kClSlices];      // entry offset of the slice's gather addresses
+  int32_t s_aoff[kClSlices];      // entry offset of the slice's gather codes
   int64_t s_base[kClSlices];      // first entry of the slice in the global block-SELL arrays
 #ifdef FEA_CLUSTER_PROFILE
   long long prof[10];
@@ -90,27 +93,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ double2 ld_cluster_f64x2(uint32_t addr) {
-  double2 v;
-  asm volatile("ld.shared::cluster.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ double2 ld_shared_f64x2(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-// gather of a published p entry from its 16-bit code: bits 0-10 row inside the owning CTA, bits
-// 11-13 rank of that CTA, bit 15 set for an entry of ANOTHER CTA (distributed shared memory,
-// ~20 B/clk per SM); own entries use the plain 128 B/clk path.  Two bytes per block instead of a
-// 4-byte address leave room for ~10 % more matrix blocks in shared memory.
-__device__ __forceinline__ double2 ld_p(uint32_t code, uint32_t pbuf_a) {
-  const uint32_t la = pbuf_a + 16u * (code & 0x7ffu);
-  return (code & 0x8000u) ? ld_cluster_f64x2(mapa_u32(la, (code >> 11) & 7u)) : ld_shared_f64x2(la);
-}
-__device__ __forceinline__ double ld_cluster_f64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ int ld_cluster_s32(uint32_t addr) {
@@ -118,24 +103,22 @@ __device__ __forceinline__ int ld_cluster_s32(uint32_t addr) {
   asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+__device__ __forceinline__ void st_cluster_s32(uint32_t addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// Dot products over the cluster, push model: lane c < CL of every warp stores the warp's partial
-// into slot [rank][warp] of CTA c's table; once all CL x 16 partials of a phase have landed every
-// warp of every CTA adds the slots of its own copy in the same fixed order, so all of them hold the
-// same bits and no intra-CTA broadcast is needed.
-//
-// "Landed" is signalled without a cluster barrier: the partial travels as st.async, which adds its
-// 8 bytes to the transaction count of an mbarrier in the DESTINATION CTA; every thread waits on its
-// own CTA's mbarrier (try_wait, acquire at cluster scope).  Compared with barrier.cluster this needs
-// no release fence over the CTA's earlier stores and no cluster-wide rendezvous.  A phase cannot be
-// overtaken: the partials of iteration k+1 are pushed after the S1 barrier of k+1, which every
-// thread reaches only after it has consumed phase k; thread 0 re-arms the barrier (arrive +
-// expect_tx) as soon as it has seen a phase complete -- partials that arrive before that only make
-// the transaction count transiently negative while the pending arrival keeps the phase open.
+// ---- synchronisation inside an iteration: transaction barriers, no cluster barrier --------------
+// Everything a CTA needs from its peers in an iteration -- the dot-product partials and the halo
+// of the search direction -- is PUSHED into its shared memory with st.async, which adds the bytes
+// it delivers to the transaction count of an mbarrier in the DESTINATION CTA.  A thread that sees
+// the phase complete (try_wait, acquire at cluster scope) sees the data.  Compared with
+// barrier.cluster this needs no release fence (cg::cluster_group::sync() compiles to MEMBAR.ALL.GPU
+// + ERRBAR before the arrive: measured 7 % of the solve for the one barrier that published p) and
+// no cluster-wide rendezvous.  Each barrier has one pending arrival per phase: thread 0 of the
+// waiting CTA arrives with expect_tx(bytes) just before it waits; bytes that land earlier only make
+// the transaction count transiently negative.  A phase cannot be overtaken: the pushes of iteration
+// k+1 follow the sender's wait on the r.r partials of iteration k, which every warp of the cluster
+// has pushed only after its last gather of iteration k.
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
@@ -153,9 +136,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(mbar), "r"(parity) : "memory");
 }
+// all `bytes` of the phase have landed in this CTA (parity = phases of this barrier seen so far, mod 2)
+__device__ __forceinline__ void await_tx(uint64_t* mbar, uint32_t bytes, uint32_t parity, int tid) {
+  const uint32_t a = smem_u32(mbar);
+  if (tid == 0) mbar_arm(a, bytes);
+  mbar_wait(a, parity);
+}
+
+// Dot products over the cluster, push model: lane c < CL of every warp sends the warp's partial to
+// slot [rank][warp] of CTA c's table; once all CL x 16 partials have landed every warp of every CTA
+// adds the slots of its own copy in the same fixed order, so all of them hold the same bits and no
+// intra-CTA broadcast is needed.
 template <int CL>
 __device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, uint32_t mbar_off, int rank, int warp, int lane, double v) {
-#if FEA_CL_ASYNC_RED
   if (lane < CL) {
     const uint32_t base = mapa_u32(smem_u32(h), lane);   // the header of CTA `lane`
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(
@@ -163,19 +156,6 @@ __device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, ui
                  "d"(v), "r"(base + mbar_off)
                  : "memory");
   }
-#else
-  if (lane < CL) st_cluster_f64(mapa_u32(smem_u32(h) + field_off + 8u * (uint32_t)(rank * kClW + warp), lane), v);
-#endif
-}
-// all partials of the phase are in this CTA's table (parity = phases of this barrier seen so far, mod 2)
-template <int CL>
-__device__ __forceinline__ void await_partials(cg::cluster_group& cluster, ClHeader* h, uint64_t* mbar, uint32_t parity, int tid) {
-#if FEA_CL_ASYNC_RED
-  mbar_wait(smem_u32(mbar), parity);
-  if (tid == 0) mbar_arm(smem_u32(mbar), 8u * CL * kClW);
-#else
-  cluster.sync();
-#endif
 }
 template <int CL>
 __device__ __forceinline__ double sum_table(const double* t, int lane) {
@@ -184,23 +164,6 @@ __device__ __forceinline__ double sum_table(const double* t, int lane) {
   for (int i = 0; i < (CL * kClW + 31) / 32; ++i)
     if (lane + 32 * i < CL * kClW) acc += t[lane + 32 * i];
   return warp_sum(acc);
-}
-
-// S1: the p entries every thread wrote into its CTA's shared memory become visible to the gathers
-// of the whole cluster.
-__device__ __forceinline__ void publish_sync(cg::cluster_group& cluster, int tid) {
-#if FEA_CL_S1_MODE == 1
-  __syncthreads();
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-#elif FEA_CL_S1_MODE == 2
-  // one release fence per CTA instead of one per thread: bar.sync orders the CTA's stores before
-  // thread 0's fence (cumulativity), the fence + relaxed arrive form the release pattern
-  __syncthreads();
-  if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-  asm volatile("barrier.cluster.arrive.relaxed;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-#else
-  cluster.sync();
-#endif
 }
 
 template <int CL>
@@ -215,17 +178,15 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  uint32_t phase = 0;   // bit 0 / bit 1: parity of the p.q / r.r barrier phase that is awaited next
-#if FEA_CL_ASYNC_RED
+  const uint32_t smem_a = smem_u32(smem);
+  uint32_t phase = 0;   // bits 0 / 1 / 2: parity of the next p.q / r.r / halo phase
   if (tid == 0) {
     mbar_init(smem_u32(&h->mbarA), 1);
     mbar_init(smem_u32(&h->mbarB), 1);
+    mbar_init(smem_u32(&h->mbarP), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_arm(smem_u32(&h->mbarA), 8u * CL * kClW);
-    mbar_arm(smem_u32(&h->mbarB), 8u * CL * kClW);
   }
-  // (the first cluster.sync() of the queue loop below orders the initialisation before any push)
-#endif
+  // (the first cluster.sync() of the queue loop orders the initialisation before any push)
 
   for (;;) {
     // ---- next system of the queue (rank 0 pulls, everyone reads it through DSMEM) --------------
@@ -246,55 +207,166 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     const int Rc = Sc * 32;                                        // rows per CTA
     const int my_sl = max(0, min(Sc, n_sl - rank * Sc));           // slices this CTA owns
     const int64_t my_row0 = row0 + (int64_t)rank * Rc;
-    double2* pbuf = reinterpret_cast<double2*>(smem + kHdr);       // [Rc] published p
-    double* dcs = reinterpret_cast<double*>(smem + kHdr + Rc * 16); // [Rc] diagonal-block couplings
-    const int mat0 = kHdr + ((Rc * 24 + 127) / 128) * 128;         // matrix area
-    const int cap = kClSmemBytes - mat0;
 
-    // ---- slice table + copy of the CTA's matrix slices into shared memory ------------------------
-    // gather codes (2 B per block) of ALL owned slices are kept on chip; the 32-byte blocks of
-    // as many slices as fit follow them, the rest is streamed from global memory (L2) every iteration
+    // ---- halo: which rows of other CTAs do my rows gather? ----------------------------------------
+    // One bit per row of the system (word w = slice w of the system).  The marked rows, in row
+    // order, become halo slots Rc, Rc+1, ... of this CTA's p buffer; their owners get a send list.
+    uint32_t* bmp = reinterpret_cast<uint32_t*>(smem + kClSmemBytes - kClTmpBytes);
+    int32_t* pre = reinterpret_cast<int32_t*>(bmp) + kClWords;     // [kClWords + 1] exclusive prefix of popc
     if (tid < kClSlices) {
       h->s_len[tid] = tid < my_sl ? P.slice_len[(my_row0 >> 5) + tid] : 0;
       h->s_base[tid] = tid < my_sl ? P.slice_ptr[(my_row0 >> 5) + tid] : 0;
     }
+    bmp[tid] = 0;
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kClRpt; ++k) {
+      const int ls = warp + kClW * k;        // local slice handled by this warp
+      if (ls >= my_sl) continue;
+      const int L = h->s_len[ls];
+      const int64_t base = h->s_base[ls];
+      for (int j = 0; j < L; ++j) {
+        const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;   // row inside the system
+        if (c / Rc != rank) atomicOr(&bmp[c >> 5], 1u << (c & 31));
+      }
+    }
+    __syncthreads();
+    int H;                                   // halo rows of this CTA
+    {
+      const uint32_t wbits = bmp[tid];
+      int incl = __popc(wbits);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) h->wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      H = 0;
+#pragma unroll
+      for (int w = 0; w < kClW; ++w) {
+        const int t = h->wsum[w];
+        woff += w < warp ? t : 0;
+        H += t;
+      }
+      pre[tid] = woff + incl - __popc(wbits);
+      if (tid == 0) pre[kClWords] = H;
+      __syncthreads();
+    }
+    if (tid < kCl)   // tell every owner how many of its rows I gather (0 for myself)
+      st_cluster_s32(mapa_u32(smem_u32(&h->send_from[rank]), tid),
+                     pre[min((tid + 1) * Sc, kClWords)] - pre[min(tid * Sc, kClWords)]);
+    cluster.sync();                                                // #1: send_from[] complete
+
+    // ---- layout of the shared memory (depends on the halo and send-list sizes) -------------------
+    //   header | send list [n_send] u32 | p: own rows [Rc] + halo [H] double2 | dcoup [Rc] f64 |
+    //   gather codes of all owned slices (u16 index into p) | 2x2 blocks of the resident slices
+    if (tid < kCl) {
+      int off = 0;
+      for (int c = 0; c < rank; ++c) off += ld_cluster_s32(mapa_u32(smem_u32(&h->send_from[c]), tid));
+      h->seg_off[tid] = off;
+    }
     if (tid == 0) {
+      int S = 0;
+      for (int c = 0; c < kCl; ++c) S += h->send_from[c];
+      h->n_send = S;
       int ent = 0;
       for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += h->s_len[i] * 32; }
+      const int off_pbuf = kHdr + (4 * S + 127) / 128 * 128;
+      const int mat0 = (off_pbuf + 16 * (Rc + H) + 8 * Rc + 127) / 128 * 128;
       int off = (ent * 2 + 127) / 128 * 128;
-      // slice order: the first slices (round k = 0 of every warp) are resident.  (Measured against
+      const int fit = (mat0 + off <= kClSmemBytes - kClTmpBytes && Rc + H <= 0xffff && H <= P.cl_halo_cap) ? 1 : 0;
+      h->off_pbuf = off_pbuf;
+      h->mat0 = mat0;
+      // resident slices: the first slices (round k = 0 of every warp) are resident.  (Measured against
       // giving whole warps resident slices, 48.5 ms, and a warp/round checkerboard, 49.9 ms: 47.2 ms.)
+      const int cap = kClSmemBytes - mat0;
       for (int i = 0; i < kClSlices; ++i) {
         const int bytes = h->s_len[i] * 32 * 32;
         if (i < my_sl && off + bytes <= cap) { h->s_off[i] = off; off += bytes; }
         else h->s_off[i] = -1;
       }
+      for (int c = 0; c < kCl; ++c) st_cluster_s32(mapa_u32(smem_u32(&h->fit[rank]), c), fit);
     }
-    __syncthreads();
+    cluster.sync();                                                // #2: fit[] complete, layout visible
+    {
+      bool ok = true;
+#pragma unroll
+      for (int c = 0; c < kCl; ++c) ok = ok && h->fit[c] != 0;
+      if (!ok) {   // (uniform) halo too large for the shared memory: left to the streaming kernels
+        if (rank == 0 && tid == 0) atomicAdd(P.cl_counter + 10, 1);
+        continue;
+      }
+    }
+    const int off_pbuf = h->off_pbuf, mat0 = h->mat0;
+    double2* pbuf = reinterpret_cast<double2*>(smem + off_pbuf);   // [Rc] published p + [H] halo
+    double* dcs = reinterpret_cast<double*>(pbuf + Rc + H);        // [Rc] diagonal-block couplings
     const uint32_t pbuf_a = smem_u32(pbuf);
     uint16_t* sa_all = reinterpret_cast<uint16_t*>(smem + mat0);
+    const uint32_t* sendl = reinterpret_cast<const uint32_t*>(smem + kHdr);
+
+    // ---- gather codes: index into p (own row, or halo slot of a row owned by another CTA) --------
 #pragma unroll
     for (int k = 0; k < kClRpt; ++k) {
-      const int ls = warp + kClW * k;        // local slice handled by this warp
+      const int ls = warp + kClW * k;
       if (ls >= my_sl) continue;
-      const int off = h->s_off[ls];
       const int L = h->s_len[ls];
       const int64_t base = h->s_base[ls];
       uint16_t* sa = sa_all + h->s_aoff[ls];
+      bool remote = false;
+      for (int j = 0; j < L; ++j) {
+        const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;
+        const int cr = c / Rc;
+        const int code = cr == rank ? c - cr * Rc
+                                    : Rc + pre[c >> 5] + __popc(bmp[c >> 5] & ((1u << (c & 31)) - 1u));
+        remote = remote || cr != rank;
+        sa[j * 32 + lane] = (uint16_t)code;
+      }
+      remote = __any_sync(0xffffffffu, remote);
+      if (lane == 0) h->s_halo[ls] = remote ? 1 : 0;
+    }
+    // ---- send lists: one entry per halo row, written into its owner's list -----------------------
+    // entry = row inside the owner (11 bits) | consumer rank (3 bits) | consumer's p slot (>> 4 of
+    // the byte offset in ITS shared memory: the layouts of the CTAs differ)
+    {
+      uint32_t bits = bmp[tid];
+      if (bits) {
+        const int o = tid / Sc;
+        int slot = pre[tid];
+        int pos = h->seg_off[o] + slot - pre[min(o * Sc, kClWords)];
+        const int lr0 = (tid - o * Sc) * 32;
+        const uint32_t dst = mapa_u32(smem_a + kHdr, o);
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const uint32_t e = (uint32_t)(lr0 + b) | ((uint32_t)rank << 11) | ((uint32_t)(off_pbuf / 16 + Rc + slot) << 14);
+          st_cluster_s32(dst + 4u * (uint32_t)pos, (int)e);
+          ++slot;
+          ++pos;
+        }
+      }
+    }
+    cluster.sync();                                                // #3: send lists complete; bitmap dead
+    const int n_send = h->n_send;
+
+    // ---- 2x2 blocks of the resident slices --------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kClRpt; ++k) {
+      const int ls = warp + kClW * k;
+      if (ls >= my_sl) continue;
+      const int off = h->s_off[ls];
+      if (off < 0) continue;
+      const int L = h->s_len[ls];
+      const int64_t base = h->s_base[ls];
       // values per slice: L x 32 top halves (k00,k01) then L x 32 bottom halves (k10,k11)
       // (16-byte lane stride: conflict-free 128-bit shared loads)
-      double2* st = reinterpret_cast<double2*>(smem + mat0 + (off < 0 ? 0 : off));
+      double2* st = reinterpret_cast<double2*>(smem + mat0 + off);
       double2* sb = st + L * 32;
       for (int j = 0; j < L; ++j) {
-        if (off >= 0) {
-          const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
-          st[j * 32 + lane] = make_double2(blk.x, blk.y);
-          sb[j * 32 + lane] = make_double2(blk.z, blk.w);
-        }
-        const int c = ld_stream_i32(P.col + base + j * 32 + lane) - (int)row0;   // row inside the system
-        const int cr = c / Rc;
-        sa[j * 32 + lane] = (uint16_t)((c - cr * Rc) | (cr << 11) | (cr == rank ? 0 : 0x8000));
+        const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
+        st[j * 32 + lane] = make_double2(blk.x, blk.y);
+        sb[j * 32 + lane] = make_double2(blk.z, blk.w);
       }
     }
 
@@ -369,7 +441,22 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
       }
       PROF_T(0);
-      publish_sync(cluster, tid);                               // S1: every CTA's p is visible
+      // S1: the CTA's new p is complete (bar.sync) and its boundary rows are pushed into the halo
+      // slots of the CTAs that gather them.  A warp waits for this CTA's own halo only when it reaches
+      // a slice that gathers from it (the few slices along the CTA's borders) or at the end of its
+      // SpMV: the flight time of the pushes is hidden behind the interior slices.
+      __syncthreads();
+      for (int i = tid; i < n_send; i += kClT) {
+        const uint32_t e = sendl[i];
+        const double2 v = pbuf[e & 0x7ffu];
+        const uint32_t base = mapa_u32(smem_a, (e >> 11) & 7u);
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(
+                         base + 16u * (e >> 14)),
+                     "d"(v.x), "d"(v.y), "r"(base + (uint32_t)offsetof(ClHeader, mbarP))
+                     : "memory");
+      }
+      if (tid == 0) mbar_arm(smem_u32(&h->mbarP), 16u * (uint32_t)H);
+      bool halo_here = false;
       PROF_T(1);
       double2 q[kClRpt];
       double part = 0.0;
@@ -387,6 +474,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           const int off = h->s_off[ls];
           const uint16_t* sa = sa_all + h->s_aoff[ls] + lane;
           const uint32_t self = (uint32_t)(tid + kClT * k);
+          if (!halo_here && h->s_halo[ls]) {
+            mbar_wait(smem_u32(&h->mbarP), (phase >> 2) & 1u);
+            halo_here = true;
+          }
           if (off >= 0) {
             const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
             const double2* sb = st + L * 32;
@@ -396,7 +487,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
               for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u], pbuf_a) : make_double2(0.0, 0.0);
+              for (int u = 0; u < 4; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 if (j + u < L) {
@@ -420,7 +511,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
               for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = (j + u < L) ? ld_p(g[u], pbuf_a) : make_double2(0.0, 0.0);
+              for (int u = 0; u < 4; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
@@ -432,11 +523,13 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         q[k] = make_double2(a0, a1);
         part += own[k] ? fma(pk.x, a0, pk.y * a1) : 0.0;
       }
+      if (!halo_here) mbar_wait(smem_u32(&h->mbarP), (phase >> 2) & 1u);   // every thread consumes every phase
+      phase ^= 4u;
       if (!check) {
         part = warp_sum(part);
         push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partA), (uint32_t)offsetof(ClHeader, mbarA), rank, warp, lane, part);
         PROF_T(2);
-        await_partials<CL>(cluster, h, &h->mbarA, phase & 1u, tid);   // S2: p.q partials visible
+        await_tx(&h->mbarA, 8u * CL * kClW, phase & 1u, tid);       // S2: p.q partials have landed
         phase ^= 1u;
         PROF_T(3);
         const double pq = sum_table<CL>(h->partA, lane);
@@ -468,13 +561,14 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       part = warp_sum(part);
       push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), (uint32_t)offsetof(ClHeader, mbarB), rank, warp, lane, part);
       PROF_T(5);
-      await_partials<CL>(cluster, h, &h->mbarB, (phase >> 1) & 1u, tid);   // S3: r.r partials visible
+      await_tx(&h->mbarB, 8u * CL * kClW, (phase >> 1) & 1u, tid);  // S3: r.r partials have landed
       phase ^= 2u;
       PROF_T(6);
       const double rz_new = sum_table<CL>(h->partB, lane);
       PROF_T(7);
       if (monitor) {
-        // all gathers of x are done (S3): put p back; continue CG with the true residual as r
+        // every gather of x is done (S3; the halo copies are refreshed by the next push): put p back
+        // and continue CG with the true residual as r
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k)
           if (own[k]) pbuf[tid + kClT * k] = P.q[my_row0 + tid + kClT * k];
@@ -533,7 +627,6 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       P.rz_last[s] = rz;
       atomicAdd(P.sc.n_done, 1);
     }
-    cluster.sync();   // nobody may still be reading this CTA's shared memory when it is reused
   }
 }
 

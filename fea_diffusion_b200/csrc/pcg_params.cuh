@@ -36,7 +36,9 @@ struct PcgPtrs {
   const int32_t* cl_order;  // eligible systems grouped by class; largest first in each
   int32_t cl_off[9];        // first entry of each class in cl_order (index = CTAs per cluster)
   int32_t cl_cnt[9];        // entries of each class (0 = class not launched)
-  int32_t* cl_counter;      // [1..8] work-queue heads, [0] restarts (device counters, zeroed per solve)
+  int32_t* cl_counter;      // [1..8] work-queue heads, [0] restarts, [10] systems handed back to the
+                            // streaming kernels (device counters, zeroed per solve)
+  int32_t cl_halo_cap;      // largest halo (rows gathered from other CTAs) a CTA accepts (test knob)
 };
 static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
 

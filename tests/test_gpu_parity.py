@@ -319,3 +319,53 @@ def test_every_cluster_size_agrees_with_the_streaming_path(nx, ny, cl):
         out[path] = r
     assert rel(out[0].u, out[1].u) <= 1e-9
     assert abs(int(out[0].iters[0]) - int(out[1].iters[0])) <= max(3, out[1].iters[0] // 200)
+
+
+def test_cluster_hands_a_system_back_when_its_halo_does_not_fit():
+    """On chip every CTA receives the rows it gathers from its peers ("halo") by pushes into its own
+    shared memory; a system whose halo does not fit is handed back to the streaming kernels.  Forced
+    here with the halo cap knob: the result must be the streaming path's, bit for bit, and a
+    single-CTA system (no halo) of the same batch must still be solved on chip."""
+    big, _ = cases.quad_plate(90, 55)      # 3-CTA cluster
+    small, _ = cases.quad_plate(48, 30)    # 1 CTA: no halo
+    res = {}
+    for name, opts in (("capped", {"cluster_halo_cap": 0}), ("stream", {"pcg_path": 1}), ("onchip", {})):
+        c = Context(0)
+        for k, v in opts.items():
+            c.set_option(k, v)
+        try:
+            with c.create_batch(pack([big.sample, small.sample])) as b:
+                res[name] = b.assemble().solve(1e-11, 200000).download()
+        finally:
+            c.close()
+        assert (res[name].status == SAMPLE_CONVERGED).all()
+    ub = [pack([big.sample, small.sample]).split_vertices(res[k].u) for k in ("capped", "stream", "onchip")]
+    assert np.array_equal(ub[0][0], ub[1][0]) and res["capped"].iters[0] == res["stream"].iters[0]
+    assert np.array_equal(ub[0][1], ub[2][1]) and res["capped"].iters[1] == res["onchip"].iters[1]
+    assert rel(ub[0][0], ub[2][0]) <= 1e-9
+
+
+def test_cluster_with_a_halo_of_thousands_of_rows():
+    """A randomly renumbered 3-CTA plate solved in INPUT order (row_order 0): nearly every row a CTA
+    gathers belongs to a peer, so halo and send lists hold thousands of entries (several passes of
+    the push loop).  Same displacements as the lattice numbering, and it still runs on chip."""
+    setup, _ = cases.quad_plate(90, 55)
+    smp = setup.sample
+    nv = len(smp.coors)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(nv)                 # new index of old vertex i
+    inv = np.empty(nv, np.int64)
+    inv[perm] = np.arange(nv)
+    shuffled = Sample(smp.coors[inv], perm[smp.conn].astype(np.int32), smp.cell_region, smp.D,
+                      np.asarray(smp.fixed)[inv], np.asarray(smp.rhs).reshape(nv, 2)[inv].reshape(np.shape(smp.rhs)))
+    c = Context(0)
+    c.set_option("row_order", 0)
+    try:
+        with c.create_batch(pack([smp, shuffled])) as b:
+            r = b.assemble().solve(1e-11, 200000).download()
+            us = b.packed.split_vertices(r.u)
+            st = b.stats()
+    finally:
+        c.close()
+    assert (r.status == SAMPLE_CONVERGED).all() and st["cluster_systems"] == 2
+    assert rel(us[1][perm], us[0]) <= 1e-9
