@@ -205,8 +205,19 @@ def run_b200(a):
     # work is identical by construction and the N-GPU figure measures the machine, not the draw of
     # plates (two 100-plate draws differ by +-15 % in PCG work); --distinct-shards gives every rank
     # its own plates instead
-    items, rejected = build_workload(a.plates, a.conditions, a.image_size,
-                                     seed0=weak_scaling_seed(a.seed, rank) if a.distinct_shards else a.seed)
+    seed0 = weak_scaling_seed(a.seed, rank) if a.distinct_shards else a.seed
+    cache = os.environ.get("FEA_BENCH_CACHE")   # tuning sessions: reuse the generated workload between runs
+    if cache:
+        import pickle
+        cache = "%s.%d.%d.%d.%d.pkl" % (cache, a.plates, a.conditions, a.image_size, seed0)
+    if cache and os.path.exists(cache):
+        with open(cache, "rb") as f:
+            items, rejected = pickle.load(f)
+    else:
+        items, rejected = build_workload(a.plates, a.conditions, a.image_size, seed0=seed0)
+        if cache and rank == 0:
+            with open(cache, "wb") as f:
+                pickle.dump((items, rejected), f)
     t_gen = time.perf_counter() - t_gen
     n = len(items)
     ctx = Context(local)

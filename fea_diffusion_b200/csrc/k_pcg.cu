@@ -35,7 +35,7 @@
 
 namespace fea {
 
-#ifdef FEA_CLUSTER_PROFILE
+#if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 void pcg_cluster_profile_dump();
 #endif
 
@@ -643,7 +643,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     int32_t h_restarts = 0;
     if ((e = cudaMemcpy(&h_restarts, b.cl_counter, sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     b.stats.refined_systems += h_restarts;
-#ifdef FEA_CLUSTER_PROFILE
+#if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
     pcg_cluster_profile_dump();
 #endif
   }

@@ -35,8 +35,10 @@ namespace cg = cooperative_groups;
 
 namespace fea {
 
-#ifdef FEA_CLUSTER_PROFILE
+#if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 __device__ unsigned long long g_cl_prof[16];
+#endif
+#ifdef FEA_CLUSTER_PROFILE
 #define PROF_T(i) do { if (prof) { const long long t_ = clock64(); h->prof[i] += t_ - h->prof[9]; h->prof[9] = t_; } } while (0)
 #else
 #define PROF_T(i) do { } while (0)
@@ -55,6 +57,7 @@ constexpr int kClRpt = 4;                   // block rows per thread
 #ifndef FEA_CL_MONITOR
 #define FEA_CL_MONITOR 1024
 #endif
+
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
@@ -180,6 +183,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const uint32_t smem_a = smem_u32(smem);
   uint32_t phase = 0;   // bits 0 / 1 / 2: parity of the next p.q / r.r / halo phase
+#ifdef FEA_CLUSTER_ACCOUNT
+  const long long acc_t0 = clock64();   // SM-cycle accounting: CTA lifetime / system set-up / iterations
+#endif
   if (tid == 0) {
     mbar_init(smem_u32(&h->mbarA), 1);
     mbar_init(smem_u32(&h->mbarB), 1);
@@ -199,6 +205,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     }
     const int s = P.cl_order[P.cl_off[kClass] + qi];
     if (P.sc.done[s]) { cluster.sync(); continue; }   // empty / zero-load systems (init_scalars)
+#ifdef FEA_CLUSTER_ACCOUNT
+    const long long acc_t1 = clock64();
+#endif
 
     // ---- geometry of the system inside the cluster ----------------------------------------------
     const int64_t row0 = (int64_t)P.cta_first[s] * kCtaRows;       // first block row of the system
@@ -401,6 +410,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     }
     __syncthreads();
     int iters = 0, status = FEA_SAMPLE_NOT_RUN;
+#ifdef FEA_CLUSTER_ACCOUNT
+    const long long acc_t2 = clock64();
+#endif
     bool restarted = false;
     bool monitored = false;                   // the monitor pass of the current iteration count is done
 
@@ -619,6 +631,15 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       atomicAdd(&g_cl_prof[8], (unsigned long long)iters);
     }
 #endif
+#ifdef FEA_CLUSTER_ACCOUNT
+    if (tid == 0) {
+      const long long t3 = clock64();
+      atomicAdd(&g_cl_prof[10], (unsigned long long)(acc_t2 - acc_t1));
+      atomicAdd(&g_cl_prof[11], (unsigned long long)(t3 - acc_t2));
+      if (rank == 0) atomicAdd(&g_cl_prof[12], 1ull);
+      if (rank == 0) atomicAdd(&g_cl_prof[14], (unsigned long long)iters * CL);
+    }
+#endif
     if (rank == 0 && tid == 0) {
       P.sc.iters[s] = iters;
       P.sc.status[s] = status;
@@ -628,6 +649,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       atomicAdd(P.sc.n_done, 1);
     }
   }
+#ifdef FEA_CLUSTER_ACCOUNT
+  if (tid == 0) atomicAdd(&g_cl_prof[13], (unsigned long long)(clock64() - acc_t0));
+#endif
 }
 
 typedef void (*cluster_fn)(const PcgPtrs*);
@@ -679,10 +703,15 @@ int pcg_cluster_capacity(Ctx& c, int cl) {
   return n;
 }
 
-#ifdef FEA_CLUSTER_PROFILE
+#if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 void pcg_cluster_profile_dump() {
   unsigned long long h[16];
   cudaMemcpyFromSymbol(h, g_cl_prof, sizeof(h));
+#ifdef FEA_CLUSTER_ACCOUNT
+  fprintf(stderr, "[cluster account] systems %llu  set-up %.3f SM-Mcycles  iterating %.3f SM-Mcycles  CTA lifetime %.3f SM-Mcycles  "
+                  "iterations x CTAs %llu  (cycles per iteration %.0f)\n",
+          h[12], h[10] * 1e-6, h[11] * 1e-6, h[13] * 1e-6, h[14], h[14] ? (double)h[11] / (double)h[14] : 0.0);
+#endif
   const char* names[8] = {"p publish", "S1 barrier", "spmv + warp partial", "S2 barrier", "sum A", "update", "S3 barrier", "sum B"};
   const double it = (double)(h[8] ? h[8] : 1);
   for (int i = 0; i < 8; ++i) fprintf(stderr, "[cluster prof] %-20s %8.0f cycles/iter\n", names[i], h[i] / it);

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 def child(path, reps):
     from fea_diffusion_b200 import Context, pack
     with open(path, "rb") as f:
-        samples = pickle.load(f)
+        samples = pickle.load(f) * int(os.environ.get("AB_DUP", "1"))
     ctx = Context(0)
     packed = pack(samples, alloc=ctx.pinned_empty)
     ms = []
@@ -43,6 +43,7 @@ def main():
         k = args.pop(0)
         v = int(args.pop(0))
         if k == "--plates": plates = v
+        elif k == "--dup": os.environ["AB_DUP"] = str(v)   # solve the workload v times over in ONE batch
         elif k == "--reps": reps = v
     if args and args[0] == "__child__":
         return child(args[1], int(args[2]))
