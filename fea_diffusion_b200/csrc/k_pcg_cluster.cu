@@ -11,19 +11,24 @@
 //     slices and the 2x2 blocks of as many slices as fit are copied from HBM to shared memory ONCE,
 //     the blocks of the other slices are streamed from L2 every iteration;
 //   * x, r of a thread's (up to 4) block rows live in registers for the whole solve;
-//   * the search direction p is published in shared memory and gathered by the neighbours --
-//     plain ld.shared inside the CTA, mapa + ld.shared::cluster (distributed shared memory) across;
-//   * dot products: every warp pushes its partial into a table in all CTAs (st.shared::cluster);
-//     after the barrier every warp adds its local copy in the same fixed order -- no atomics,
-//     bitwise reproducible, independent of which cluster or SM runs the system;
-//   * three cluster barriers per iteration (p published, p.q partials, r.r partials);
+//   * the search direction p lives in the owner's shared memory.  The rows a CTA gathers from its
+//     peers (its "halo", found once per system with a bitmap + prefix sum) have slots behind its own
+//     rows, and their owners PUSH the new values into those slots every iteration (send list,
+//     st.async): every gather of the SpMV is a plain ld.shared;
+//   * dot products: every warp pushes its partial into a table in all CTAs (st.async); every warp
+//     then adds its local copy in the same fixed order -- no atomics, bitwise reproducible,
+//     independent of which cluster or SM runs the system;
+//   * NO cluster barrier inside the iteration: the three hand-overs (halo of p, p.q partials, r.r
+//     partials) complete on mbarrier transaction counts in the receiving CTA; a warp waits for the
+//     halo only when it reaches a slice that reads it;
 //   * a converged system is verified against its TRUE residual (and restarted once if the gap is
 //     material); every 1024 iterations the same pass monitors progress and stops mechanisms.
 //
 // Clusters are persistent and pull systems from a queue (longest job first), so there is no
 // lock-step and no tail of idle CTAs waiting for the slowest system of a batch.  HBM traffic is one
 // read of the matrix and vectors per SOLVE instead of per iteration.
-// Systems too large for a cluster (> 16 384 block rows) keep using the streaming kernels of k_pcg.cu.
+// Systems too large for a cluster (> 16 384 block rows), and systems whose halo does not fit beside
+// the matrix (handed back by the kernel), use the streaming kernels of k_pcg.cu.
 #include <cooperative_groups.h>
 
 #include <cstdio>

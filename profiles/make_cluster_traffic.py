@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""profiles/cluster_traffic.json (read by bench.py for roofline.traffic) from the ncu traffic pass of
+profiles/run_ncu.sh:  python profiles/make_cluster_traffic.py profiles/<tag>_traffic.csv <tag>"""
+import csv, json, os, re, sys
+path, tag = sys.argv[1], sys.argv[2]
+per = {}
+for r in csv.reader(open(path)):
+    if len(r) > 14 and r[0].isdigit():
+        k = re.sub(r"^void\s+|\(.*", "", r[4])
+        per.setdefault(k, {})[r[12]] = float(r[14])
+rd = sum(v["dram__bytes_read.sum"] for v in per.values())
+wr = sum(v["dram__bytes_write.sum"] for v in per.values())
+out = {
+    "kernel": "k_pcg_cluster<1..4> (the four concurrent persistent kernels of one device-resident step, profiled one after the other)",
+    "source": "profiles/%s_traffic.csv (ncu --metrics dram__bytes_*.sum,lts__t_sectors.sum,gpu__time_duration.sum) and "
+              "profiles/%s_cluster_ncu_raw.csv (--set full)" % (tag, tag),
+    "workload": "100 plates x 4 conditions, mesh_size 1e-2", "nnz": 49452160, "n_active_dofs": 3664196,
+    "per_kernel": per, "dram_bytes_read_per_launch": rd, "dram_bytes_write_per_launch": wr,
+    "dram_bytes_per_launch": rd + wr,
+    "l2_bytes_per_launch": 32.0 * sum(v["lts__t_sectors.sum"] for v in per.values()),
+}
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "cluster_traffic.json"), "w"), indent=1)
+print(json.dumps({k: out[k] for k in ("dram_bytes_per_launch", "l2_bytes_per_launch")}))
