@@ -145,6 +145,9 @@ int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
  *                   what is exported (fea_batch_get_csr always follows sfepy's numbering)
  *   "refine_rounds" restarts from the true residual per solve (default 1; 0 = the true residual
  *                   is only checked and reported)
+ *   "cluster_halo_cap"  test knob: the largest number of rows a CTA of the on-chip path accepts
+ *                   from its cluster peers (default: whatever fits its shared memory); a system
+ *                   above it is handed back to the streaming kernels
  *   "spmv_variant"  tuning knob of k_pcg_spmv;  "use_graphs" 0/1 (streaming path) */
 int  fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this context has launched so far (graph nodes included) */
