@@ -45,7 +45,6 @@ def parse():
     ap.add_argument("--image-size", type=int, default=64)
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--max-iter", type=int, default=20000)
-    ap.add_argument("--stagger", type=int, default=0, help="priority step between the e2e contexts (0 = equal priorities)")
     ap.add_argument("--streams", type=int, default=3, help="contexts (streams) the e2e path deals its steps to")
     ap.add_argument("--cpu-samples", type=int, default=8, help="bounded sample for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -280,7 +279,7 @@ def run_b200(a):
     # batch overlap the bulk of another (fea_diffusion_b200.pipeline.Pipeline) ---------------------
     from fea_diffusion_b200.pipeline import Pipeline
     a.streams = max(1, min(a.streams, a.steps // 2))   # at least two steps per stream, or there is nothing to overlap
-    pipe = Pipeline(local, a.streams, staggered_priorities=a.stagger, first=ctx)
+    pipe = Pipeline(local, a.streams, staggered_priorities=False, first=ctx)
     outs = [BatchResult(u=c.pinned_empty((packed.n_vertices, 2), np.float64), ranges=c.pinned_empty((n, 4), np.float64),
                         iters=c.pinned_empty((n,), np.int32), relres=c.pinned_empty((n,), np.float64),
                         status=c.pinned_empty((n,), np.int32), images=c.pinned_empty((n, 2, size, size), np.uint8))

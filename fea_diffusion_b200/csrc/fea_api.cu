@@ -114,7 +114,6 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   }
   if (const char* v = getenv("FEA_NO_GRAPHS")) ctx->c.use_graphs = atoi(v) ? 0 : 1;
   if (const char* v = getenv("FEA_ROW_ORDER")) ctx->c.row_order = atoi(v);
-  if (const char* v = getenv("FEA_CLUSTER_SCHED")) ctx->c.cluster_sched = std::max(0, std::min(3, atoi(v)));
   if (const char* v = getenv("FEA_CLUSTER_MIN")) ctx->c.cluster_min = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("FEA_PCG_PATH")) ctx->c.pcg_path = (strcmp(v, "stream") == 0 || atoi(v) == 1) ? 1 : 0;
   if (cudaHostAlloc((void**)&ctx->c.h_flag, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
@@ -149,11 +148,6 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   pcg_release(ctx->c);
-  for (int j = 0; j < 2; ++j)
-    for (int k = 0; k < 9; ++k) {
-      if (ctx->c.cl_stream[j][k]) cudaStreamDestroy(ctx->c.cl_stream[j][k]);
-      if (ctx->c.cl_done[j][k]) cudaEventDestroy(ctx->c.cl_done[j][k]);
-    }
   for (auto& ev : ctx->c.events) cudaEventDestroy(ev);
   cudaEventDestroy(ctx->c.ev_poll[0]);
   cudaEventDestroy(ctx->c.ev_poll[1]);
@@ -221,7 +215,6 @@ int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "pcg_path") == 0) ctx->c.pcg_path = value == 1 ? 1 : 0;
   else if (strcmp(key, "row_order") == 0) ctx->c.row_order = (value >= 1 && value <= 3) ? (int)value : 0;
   else if (strcmp(key, "cluster_halo_cap") == 0) ctx->c.cluster_halo_cap = value < 0 ? 0 : value > (1 << 30) ? (1 << 30) : (int)value;
-  else if (strcmp(key, "cluster_sched") == 0) ctx->c.cluster_sched = value < 0 ? 0 : value > 3 ? 3 : (int)value;
   else if (strcmp(key, "cluster_min") == 0) ctx->c.cluster_min = value < 1 ? 1 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "refine_rounds") == 0) ctx->c.refine_rounds = value < 0 ? 0 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;
@@ -289,14 +282,6 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
     for (int s = 0; s < ns; ++s)
       if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s], ctx->c.cluster_min) == cls) order.push_back(s);
     b.cl_cnt[cls] = (int32_t)order.size() - b.cl_off[cls];
-    // SM-work of the class: iterations x CTAs, an iteration costing a fixed part plus one per row
-    b.cl_work[cls] = 0.0;
-    for (int i = b.cl_off[cls]; i < (int)order.size(); ++i) {
-      const int s = order[i];
-      const double rows = (double)(b.vtx_off[s + 1] - b.vtx_off[s]);
-      const double it = rows > 0 ? work[s] / std::max(1.0, rows) : 0.0;   // ~ predicted iterations (x active fraction)
-      b.cl_work[cls] += it * (0.4 * cls + 0.6 * rows / 2048.0);
-    }
     std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) { return work[x] > work[y]; });
   }
   cudaStream_t st = ctx->c.stream;
@@ -327,7 +312,7 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(dalloc(b, &b.err_flag, 4));
   A(dalloc(b, &b.empty, ns));
   A(dalloc(b, &b.cl_order, ns));
-  A(dalloc(b, &b.cl_counter, 32));  // queue heads of the cluster classes, restart count, scratch, [16+k] started clusters
+  A(dalloc(b, &b.cl_counter, 16));  // queue heads of the cluster classes, restart count, scratch
   if (!order.empty()) A(cudaMemcpyAsync(b.cl_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
   A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
   A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));

@@ -40,11 +40,6 @@ struct Ctx {
   int cluster_capacity[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // co-resident clusters of c CTAs (-1 = not queried)
   int row_order = 3;                   // solver row order: 0 = input numbering, 1 = Morton, 2 = strips, 3 = auto
   int cluster_min = 1;                 // smallest cluster size used (1..8)
-  int cluster_sched = 0;               // 0: classes compete by stream priority; 1: SMs shared out by predicted work
-  cudaStream_t cl_stream[2][9] = {};   // (sched 1) primary / overflow stream of every class, created on first use
-  cudaEvent_t cl_done[2][9] = {};
-  void* fn_wait_value32 = nullptr;     // cuStreamWaitValue32 (driver entry point, looked up once); sched 3 gates launches with it
-  int wait_value_checked = 0;
   int cluster_halo_cap = 1 << 30;      // test knob: on-chip systems with a larger per-CTA halo go to the streaming path
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // cluster kernels of different classes run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -105,7 +100,6 @@ struct Batch {
   int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
   int32_t* cl_order = nullptr;       // [ns] systems of the cluster path: class 0 then class 1
   int32_t cl_off[9] = {}, cl_cnt[9] = {};   // index = CTAs per cluster
-  double cl_work[9] = {};            // predicted SM-work of every class (arbitrary unit)
   int32_t* cl_counter = nullptr;     // [16] device work-queue heads [1..8], restart count [0], scratch [9], handed back [10]
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
@@ -162,8 +156,7 @@ void pcg_release(Ctx& c);                                     // destroys the ca
 int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl);  // CTAs per cluster (1..8), 0: streaming
 int pcg_cluster_capacity(Ctx& c, int cl);                     // co-resident clusters (0 = unavailable)
 struct PcgPtrs;
-cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_clusters, int cl, cudaStream_t st,
-                               int started_slot = -1);  // n_clusters <= capacity; slot of cl_counter that counts started clusters
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st);
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status
 cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_y);
 cudaError_t launch_raster(Batch& b, double value_scale);

@@ -30,8 +30,6 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include <cuda.h>
-
 #include "fea_internal.cuh"
 #include "pcg_params.cuh"
 
@@ -507,80 +505,12 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
   if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
-    cudaMemsetAsync(b.cl_counter, 0, 32 * sizeof(int32_t), st);
+    cudaMemsetAsync(b.cl_counter, 0, 16 * sizeof(int32_t), st);
     cudaEventRecord(c.ev_c0, st);
     // one persistent kernel per cluster class, largest clusters first; classes are spread over the
     // main stream and three auxiliary streams so that their clusters are co-scheduled and small
     // clusters fill the SMs that larger ones cannot use (GPC granularity)
     cudaEventRecord(c.ev_fork, st);
-    if (c.cluster_sched >= 1) {
-      // Shares: every class gets primary clusters in proportion to its predicted work, so that all
-      // classes run side by side from the first to the last millisecond of the solve (no change-over
-      // from one class to the next, during which freed SMs wait for enough neighbours in their GPC
-      // to host a cluster of the next size).  The primaries fit on the GPU together and are placed
-      // at once, large clusters first; the rest of each class's co-residency limit is launched as an
-      // overflow kernel of the lowest priority on the same queue: its clusters only find room when a
-      // class runs dry early (the prediction is rough), and then take over its SMs.
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      double total = 0.0;
-      for (int k = 1; k <= 8; ++k) total += P.cl_cnt[k] ? b.cl_work[k] : 0.0;
-      int n_prim[9] = {}, sms = c.sm_count;
-      for (int k = 8; k >= 1; --k) {
-        if (!P.cl_cnt[k]) continue;
-        const int capn = pcg_cluster_capacity(c, k);
-        int n = total > 0 ? (int)(c.sm_count * (b.cl_work[k] / total) / k + 0.5) : 1;
-        n = std::max(1, std::min(n, std::min(capn, (int)P.cl_cnt[k])));
-        n = std::min(n, std::max(1, sms / k));
-        n_prim[k] = n;
-        sms -= n * k;
-      }
-      for (int k = 1; k <= 8 && sms > 0; ++k)   // left-over SMs: small clusters first
-        while (P.cl_cnt[k] && sms >= k && n_prim[k] < std::min(pcg_cluster_capacity(c, k), (int)P.cl_cnt[k])) { ++n_prim[k]; sms -= k; }
-      if (getenv("FEA_DEBUG_SCHED"))
-        fprintf(stderr, "[sched] primaries cl1..8: %d %d %d %d %d %d %d %d (free SMs %d)\n", n_prim[1], n_prim[2], n_prim[3],
-                n_prim[4], n_prim[5], n_prim[6], n_prim[7], n_prim[8], sms);
-      int rank_of[9] = {}, nranks = 0;   // primaries: the larger the cluster the more urgent (placed first)
-      for (int k = 8; k >= 1; --k)
-        if (P.cl_cnt[k]) rank_of[k] = nranks++;
-      // (sched 3) placement in a fixed order: the launch of every class is gated (stream memory
-      // operation) on all primary clusters of the next larger class having STARTED, i.e. being placed;
-      // the overflow kernels on the last class.  Without it the kernels become ready together and the
-      // hardware places them in a varying order: 40.4 or 62 ms per solve depending on who came first.
-      typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-      if (c.cluster_sched == 3 && !c.wait_value_checked) {
-        c.wait_value_checked = 1;
-        cudaDriverEntryPointQueryResult qr;
-        void* fn = nullptr;
-        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-          c.fn_wait_value32 = fn;
-        cudaGetLastError();
-      }
-      const bool gated = c.cluster_sched == 3 && c.fn_wait_value32 != nullptr;
-      int prev = 0;   // class whose start count gates the next launch
-      for (int pass = 0; pass < (c.cluster_sched == 2 ? 1 : 2); ++pass)
-        for (int k = 8; k >= 1; --k) {
-          if (!P.cl_cnt[k]) continue;
-          const int n = pass == 0 ? n_prim[k] : std::min(pcg_cluster_capacity(c, k), (int)P.cl_cnt[k]) - n_prim[k];
-          if (n <= 0) continue;
-          if (!c.cl_stream[pass][k]) {
-            cudaStreamCreateWithPriority(&c.cl_stream[pass][k], cudaStreamNonBlocking,
-                                         pass == 0 ? std::min(lo - 1, hi + rank_of[k]) : lo);
-            cudaEventCreateWithFlags(&c.cl_done[pass][k], cudaEventDisableTiming);
-          }
-          cudaStream_t ks = c.cl_stream[pass][k];
-          cudaStreamWaitEvent(ks, c.ev_fork, 0);
-          if (gated && prev)
-            ((wait32_fn)c.fn_wait_value32)((CUstream)ks, (CUdeviceptr)(b.cl_counter + 16 + prev), (cuuint32_t)n_prim[prev],
-                                           CU_STREAM_WAIT_VALUE_GEQ);
-          if ((e = launch_pcg_cluster(c, dP, n, k, ks, gated && pass == 0 ? 16 + k : -1)) != cudaSuccess) return e;
-          if (pass == 0) prev = k;
-          cudaEventRecord(c.cl_done[pass][k], ks);
-          cudaStreamWaitEvent(st, c.cl_done[pass][k], 0);
-          launches += 1;
-        }
-    } else {
     bool used[3] = {false, false, false};
     int slot = 0;
     for (int k = 8; k >= 1; --k) {
@@ -592,8 +522,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
         if (!used[a]) cudaStreamWaitEvent(ks, c.ev_fork, 0);
         used[a] = true;
       }
-      const int capn = pcg_cluster_capacity(c, k);
-      if ((e = launch_pcg_cluster(c, dP, P.cl_cnt[k] < capn ? P.cl_cnt[k] : capn, k, ks)) != cudaSuccess) return e;
+      if ((e = launch_pcg_cluster(c, dP, P.cl_cnt[k], k, ks)) != cudaSuccess) return e;
       launches += 1;
       ++slot;
     }
@@ -601,7 +530,6 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       if (!used[a]) continue;
       cudaEventRecord(c.ev_join[a], c.aux[a]);
       cudaStreamWaitEvent(st, c.ev_join[a], 0);
-    }
     }
     cudaEventRecord(c.ev_c1, st);
   }

@@ -175,7 +175,7 @@ __device__ __forceinline__ double sum_table(const double* t, int lane) {
 }
 
 template <int CL>
-__global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const PcgPtrs* __restrict__ Pp, int started_slot) {
+__global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
   constexpr int kCl = CL;
   constexpr int kClass = CL;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -191,9 +191,6 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #ifdef FEA_CLUSTER_ACCOUNT
   const long long acc_t0 = clock64();   // SM-cycle accounting: CTA lifetime / system set-up / iterations
 #endif
-  // (share scheduling) the host gates the launch of the next smaller class on this count: a cluster
-  // that runs has been placed
-  if (started_slot >= 0 && rank == 0 && tid == 0) atomicAdd(P.cl_counter + started_slot, 1);
   if (tid == 0) {
     mbar_init(smem_u32(&h->mbarA), 1);
     mbar_init(smem_u32(&h->mbarB), 1);
@@ -662,7 +659,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #endif
 }
 
-typedef void (*cluster_fn)(const PcgPtrs*, int);
+typedef void (*cluster_fn)(const PcgPtrs*);
 static cluster_fn cluster_kernel(int cl) {
   switch (cl) {
     case 1: return k_pcg_cluster<1>;
@@ -741,13 +738,13 @@ int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl) {
   return cl <= kClMax ? (int)cl : 0;
 }
 
-cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_clusters, int cl, cudaStream_t st, int started_slot) {
+cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st) {
   const int capn = pcg_cluster_capacity(c, cl);
-  if (capn <= 0 || n_clusters <= 0) return cudaSuccess;
+  if (capn <= 0 || n_systems <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  cluster_config(&cfg, at, cl, n_clusters < capn ? n_clusters : capn, st);
-  return cudaLaunchKernelEx(&cfg, cluster_kernel(cl), dP, started_slot);
+  cluster_config(&cfg, at, cl, n_systems < capn ? n_systems : capn, st);
+  return cudaLaunchKernelEx(&cfg, cluster_kernel(cl), dP);
 }
 
 }  // namespace fea

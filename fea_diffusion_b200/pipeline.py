@@ -15,14 +15,14 @@ from .solver import Context
 
 
 class Pipeline:
-    def __init__(self, device: int = 0, n_streams: int = 2, staggered_priorities: int = 0,
+    def __init__(self, device: int = 0, n_streams: int = 2, staggered_priorities: bool = False,
                  first: Optional[Context] = None):
         """``first`` adopts an existing context as stream 0 (closed with the pipeline)."""
         self.device = device
         self.ctxs: List[Context] = [first] if first is not None else []
         while len(self.ctxs) < n_streams:
             i = len(self.ctxs)
-            self.ctxs.append(Context(device, priority=-i * int(staggered_priorities)))
+            self.ctxs.append(Context(device, priority=(-i if staggered_priorities else 0)))
         self.pool = ThreadPoolExecutor(max_workers=n_streams)
 
     @property
