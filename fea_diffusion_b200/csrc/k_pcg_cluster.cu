@@ -58,7 +58,18 @@ constexpr int kClW = kClT / 32;             // warps per CTA
 #ifndef FEA_CL_CTAS_PER_SM
 #define FEA_CL_CTAS_PER_SM 1
 #endif
-constexpr int kClRpt = 4;                   // block rows per thread
+#ifndef FEA_CL_RPT
+#define FEA_CL_RPT 4
+#endif
+constexpr int kClRpt = FEA_CL_RPT;          // block rows per thread
+#ifndef FEA_CL_UNROLL
+#define FEA_CL_UNROLL 4
+#endif
+constexpr int kClU = FEA_CL_UNROLL;         // gathers in flight per thread (resident slices)
+#ifndef FEA_CL_UNROLL_STREAM
+#define FEA_CL_UNROLL_STREAM 4
+#endif
+constexpr int kClUs = FEA_CL_UNROLL_STREAM; // blocks in flight per thread (slices streamed from L2)
 #ifndef FEA_CL_MONITOR
 #define FEA_CL_MONITOR 1024
 #endif
@@ -66,8 +77,9 @@ constexpr int kClRpt = 4;                   // block rows per thread
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
-constexpr int kClWords = kClMax * kClSlices;   // 32-row slices of the largest system = words of the halo bitmap
-static_assert(kClWords == kClT, "the halo scan handles one bitmap word per thread");
+constexpr int kClWords = (kClMax * kClSlices + kClT - 1) / kClT * kClT;   // 32-row slices of the largest system = words of the halo bitmap (padded to whole threads)
+static_assert(kClWords % kClT == 0 && kClSlices <= kClT && kClSlices * 32 <= 4096, "the halo scan handles kClWords / kClT bitmap words per thread");
+constexpr int kClWpt = kClWords / kClT;     // bitmap words per thread (consecutive)
 constexpr int kClTmpBytes = 2 * kClWords * 4 + 128;   // halo bitmap + its prefix sums (set-up only)
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
@@ -231,7 +243,8 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       h->s_len[tid] = tid < my_sl ? P.slice_len[(my_row0 >> 5) + tid] : 0;
       h->s_base[tid] = tid < my_sl ? P.slice_ptr[(my_row0 >> 5) + tid] : 0;
     }
-    bmp[tid] = 0;
+#pragma unroll
+    for (int i = 0; i < kClWpt; ++i) bmp[tid * kClWpt + i] = 0;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kClRpt; ++k) {
@@ -247,8 +260,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     __syncthreads();
     int H;                                   // halo rows of this CTA
     {
-      const uint32_t wbits = bmp[tid];
-      int incl = __popc(wbits);
+      int mine = 0;                          // marked rows in this thread's words
+#pragma unroll
+      for (int i = 0; i < kClWpt; ++i) mine += __popc(bmp[tid * kClWpt + i]);
+      int incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -264,7 +279,12 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         woff += w < warp ? t : 0;
         H += t;
       }
-      pre[tid] = woff + incl - __popc(wbits);
+      int run = woff + incl - mine;
+#pragma unroll
+      for (int i = 0; i < kClWpt; ++i) {
+        pre[tid * kClWpt + i] = run;
+        run += __popc(bmp[tid * kClWpt + i]);
+      }
       if (tid == 0) pre[kClWords] = H;
       __syncthreads();
     }
@@ -341,20 +361,22 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       if (lane == 0) h->s_halo[ls] = remote ? 1 : 0;
     }
     // ---- send lists: one entry per halo row, written into its owner's list -----------------------
-    // entry = row inside the owner (11 bits) | consumer rank (3 bits) | consumer's p slot (>> 4 of
+    // entry = row inside the owner (12 bits) | consumer rank (3 bits) | consumer's p slot (>> 4 of
     // the byte offset in ITS shared memory: the layouts of the CTAs differ)
-    {
-      uint32_t bits = bmp[tid];
+#pragma unroll
+    for (int i = 0; i < kClWpt; ++i) {
+      const int wd = tid * kClWpt + i;
+      uint32_t bits = bmp[wd];
       if (bits) {
-        const int o = tid / Sc;
-        int slot = pre[tid];
+        const int o = wd / Sc;
+        int slot = pre[wd];
         int pos = h->seg_off[o] + slot - pre[min(o * Sc, kClWords)];
-        const int lr0 = (tid - o * Sc) * 32;
+        const int lr0 = (wd - o * Sc) * 32;
         const uint32_t dst = mapa_u32(smem_a + kHdr, o);
         while (bits) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
-          const uint32_t e = (uint32_t)(lr0 + b) | ((uint32_t)rank << 11) | ((uint32_t)(off_pbuf / 16 + Rc + slot) << 14);
+          const uint32_t e = (uint32_t)(lr0 + b) | ((uint32_t)rank << 12) | ((uint32_t)(off_pbuf / 16 + Rc + slot) << 15);
           st_cluster_s32(dst + 4u * (uint32_t)pos, (int)e);
           ++slot;
           ++pos;
@@ -465,10 +487,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       __syncthreads();
       for (int i = tid; i < n_send; i += kClT) {
         const uint32_t e = sendl[i];
-        const double2 v = pbuf[e & 0x7ffu];
-        const uint32_t base = mapa_u32(smem_a, (e >> 11) & 7u);
+        const double2 v = pbuf[e & 0xfffu];
+        const uint32_t base = mapa_u32(smem_a, (e >> 12) & 7u);
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(
-                         base + 16u * (e >> 14)),
+                         base + 16u * (e >> 15)),
                      "d"(v.x), "d"(v.y), "r"(base + (uint32_t)offsetof(ClHeader, mbarP))
                      : "memory");
       }
@@ -498,15 +520,15 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           if (off >= 0) {
             const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
             const double2* sb = st + L * 32;
-            for (int j = 0; j < L; j += 4) {   // 4 gathers in flight; the tail round is predicated
-              uint32_t g[4];
-              double2 pj[4];
+            for (int j = 0; j < L; j += kClU) {   // kClU gathers in flight; the tail round is predicated
+              uint32_t g[kClU];
+              double2 pj[kClU];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+              for (int u = 0; u < kClU; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
+              for (int u = 0; u < kClU; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < kClU; ++u) {
                 if (j + u < L) {
                   const double2 kt = st[(j + u) * 32], kb = sb[(j + u) * 32];
                   a0 = fma(kt.x, pj[u].x, a0); a0 = fma(kt.y, pj[u].y, a0);
@@ -516,21 +538,21 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
             }
           } else {  // blocks that did not fit: streamed from global memory (L2 resident), 4 in flight
             const d4* vt = P.val + h->s_base[ls] + lane;
-            for (int j = 0; j < L; j += 4) {
-              d4 kv[4];
+            for (int j = 0; j < L; j += kClUs) {
+              d4 kv[kClUs];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < kClUs; ++u) {
                 kv[u].x = kv[u].y = kv[u].z = kv[u].w = 0.0;
                 if (j + u < L) kv[u] = ld_stream_d4(vt + (j + u) * 32);
               }
-              uint32_t g[4];
-              double2 pj[4];
+              uint32_t g[kClUs];
+              double2 pj[kClUs];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+              for (int u = 0; u < kClUs; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
+              for (int u = 0; u < kClUs; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < kClUs; ++u) {
                 a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
                 a1 = fma(kv[u].z, pj[u].x, a1); a1 = fma(kv[u].w, pj[u].y, a1);
               }
