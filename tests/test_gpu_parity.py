@@ -369,3 +369,27 @@ def test_cluster_with_a_halo_of_thousands_of_rows():
         c.close()
     assert (r.status == SAMPLE_CONVERGED).all() and st["cluster_systems"] == 2
     assert rel(us[1][perm], us[0]) <= 1e-9
+
+
+@pytest.mark.parametrize("cmin", [2, 5, 8])
+def test_cluster_min_runs_small_systems_on_oversized_clusters(cmin):
+    """``cluster_min`` forces larger clusters than a system needs: CTAs that own no rows at all (a
+    128-row system on 8 CTAs) still take part in every hand-over of the iteration.  Same result as
+    the default cluster to rounding."""
+    tiny, _ = cases.quad_plate(12, 8)          # 117 vertices: one 32-row slice per CTA at most
+    mid, _ = cases.quad_plate(70, 42)          # 2-CTA system by default
+    small, _ = cases.quad_plate(48, 30)        # 1 CTA by default
+    smp = [tiny.sample, mid.sample, small.sample]
+    res = {}
+    for k in (1, cmin):
+        c = Context(0)
+        c.set_option("cluster_min", k)
+        try:
+            with c.create_batch(pack(smp)) as b:
+                res[k] = b.assemble().solve(1e-11, 200000).download()
+                st = b.stats()
+        finally:
+            c.close()
+        assert (res[k].status == SAMPLE_CONVERGED).all() and st["cluster_systems"] == 3
+    assert rel(res[cmin].u, res[1].u) <= 1e-9
+    assert np.abs(res[cmin].iters.astype(int) - res[1].iters.astype(int)).max() <= 5
