@@ -70,6 +70,7 @@ constexpr int kClU = FEA_CL_UNROLL;         // gathers in flight per thread (res
 #define FEA_CL_UNROLL_STREAM 4
 #endif
 constexpr int kClUs = FEA_CL_UNROLL_STREAM; // blocks in flight per thread (slices streamed from L2)
+static_assert(kClU % 4 == 0 && kClUs % 4 == 0, "gather codes are fetched four at a time");
 #ifndef FEA_CL_MONITOR
 #define FEA_CL_MONITOR 1024
 #endif
@@ -100,7 +101,7 @@ struct ClHeader {                 // start of the dynamic shared memory of every
   int32_t s_halo[kClSlices];      // the slice gathers rows of other CTAs (its warp waits for the halo first)
   int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
   int32_t s_len[kClSlices];       // blocks per row of the slice
-  int32_t s_aoff[kClSlices];      // entry offset of the slice's gather codes
+  int32_t s_aoff[kClSlices];      // entry offset of the slice's gather codes (groups of 4 per lane: [L/4][32][4] u16)
   int64_t s_base[kClSlices];      // first entry of the slice in the global block-SELL arrays
 #ifdef FEA_CLUSTER_PROFILE
   long long prof[10];
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       for (int c = 0; c < kCl; ++c) S += h->send_from[c];
       h->n_send = S;
       int ent = 0;
-      for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += h->s_len[i] * 32; }
+      for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += (h->s_len[i] + 3) / 4 * 128; }
       const int off_pbuf = kHdr + (4 * S + 127) / 128 * 128;
       const int mat0 = (off_pbuf + 16 * (Rc + H) + 8 * Rc + 127) / 128 * 128;
       int off = (ent * 2 + 127) / 128 * 128;
@@ -355,8 +356,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         const int code = cr == rank ? c - cr * Rc
                                     : Rc + pre[c >> 5] + __popc(bmp[c >> 5] & ((1u << (c & 31)) - 1u));
         remote = remote || cr != rank;
-        sa[j * 32 + lane] = (uint16_t)code;
+        sa[((j >> 2) * 32 + lane) * 4 + (j & 3)] = (uint16_t)code;   // one 8-byte load fetches 4 codes of a lane
       }
+      for (int j = L; j < (L + 3) / 4 * 4; ++j)                      // tail of the last group: the own row
+        sa[((j >> 2) * 32 + lane) * 4 + (j & 3)] = (uint16_t)(ls * 32 + lane);
       remote = __any_sync(0xffffffffu, remote);
       if (lane == 0) h->s_halo[ls] = remote ? 1 : 0;
     }
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           a1 = fma(dck, pk.x, pk.y);
           const int L = h->s_len[ls];
           const int off = h->s_off[ls];
-          const uint16_t* sa = sa_all + h->s_aoff[ls] + lane;
+          const uint2* sa = reinterpret_cast<const uint2*>(sa_all + h->s_aoff[ls]) + lane;   // 4 codes per load
           const uint32_t self = (uint32_t)(tid + kClT * k);
           if (!halo_here && h->s_halo[ls]) {
             mbar_wait(smem_u32(&h->mbarP), (phase >> 2) & 1u);
@@ -524,7 +527,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
               uint32_t g[kClU];
               double2 pj[kClU];
 #pragma unroll
-              for (int u = 0; u < kClU; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+              for (int u = 0; u < kClU; u += 4) {
+                const uint2 cc = (u == 0 || j + u < L) ? sa[((j + u) >> 2) * 32] : make_uint2(self | (self << 16), self | (self << 16));
+                g[u] = cc.x & 0xffffu; g[u + 1] = cc.x >> 16; g[u + 2] = cc.y & 0xffffu; g[u + 3] = cc.y >> 16;
+              }
 #pragma unroll
               for (int u = 0; u < kClU; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
@@ -548,7 +554,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
               uint32_t g[kClUs];
               double2 pj[kClUs];
 #pragma unroll
-              for (int u = 0; u < kClUs; ++u) g[u] = (j + u < L) ? sa[(j + u) * 32] : self;
+              for (int u = 0; u < kClUs; u += 4) {
+                const uint2 cc = (u == 0 || j + u < L) ? sa[((j + u) >> 2) * 32] : make_uint2(self | (self << 16), self | (self << 16));
+                g[u] = cc.x & 0xffffu; g[u + 1] = cc.x >> 16; g[u + 2] = cc.y & 0xffffu; g[u + 3] = cc.y >> 16;
+              }
 #pragma unroll
               for (int u = 0; u < kClUs; ++u) pj[u] = ld_shared_f64x2(pbuf_a + 16u * g[u]);
 #pragma unroll
