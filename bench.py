@@ -101,6 +101,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_field(name, key):
+    """a field of a committed ncu summary under profiles/ (None if absent)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name))).get(key)
+    except Exception:
+        return None
+
+
 def ncu_traffic(info, name):
     """dram bytes per launch from the committed ncu capture, if it was taken on this workload."""
     p = os.path.join(ROOT, "profiles", name)
@@ -328,6 +336,7 @@ def run_b200(a):
                               "exceeds the HBM peak by design; HBM-streaming figures of the same iterations are in "
                               "'streaming_path'",
                     "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"],
+                    "onchip_pipe": ncu_field("cluster_traffic.json", "onchip_pipe"),
                     "l2_read_peak_gbs": 17900.0, "hbm_read_peak_gbs": 6880.0,
                     "peaks_note": "L2-resident / HBM-resident read bandwidth measured with tools/l2_bw.cu on a B200 of this pool"}
     else:

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """profiles/cluster_traffic.json (read by bench.py for roofline.traffic) from the ncu traffic pass of
-profiles/run_ncu.sh:  python profiles/make_cluster_traffic.py profiles/<tag>_traffic.csv <tag>"""
+profiles/run_ncu.sh:  python profiles/make_cluster_traffic.py profiles/<tag>_traffic.csv <tag>
+(the L1TEX / issue figures of profiles/<tag>_cluster_ncu_raw.csv are added as "onchip_pipe" when that file exists)"""
 import csv, json, os, re, sys
 path, tag = sys.argv[1], sys.argv[2]
 per = {}
@@ -19,5 +20,18 @@ out = {
     "dram_bytes_per_launch": rd + wr,
     "l2_bytes_per_launch": 32.0 * sum(v["lts__t_sectors.sum"] for v in per.values()),
 }
+raw = os.path.join(os.path.dirname(os.path.abspath(__file__)), "%s_cluster_ncu_raw.csv" % tag)
+if os.path.exists(raw):
+    rows = list(csv.reader(open(raw)))
+    hdr = rows[0]
+    pipe = {}
+    for r in rows[2:]:
+        pipe[re.sub(r"^void\s+|\(.*", "", r[0])] = {
+            "l1tex_pct_of_peak_elapsed": float(r[hdr.index("l1tex__throughput.avg.pct_of_peak_sustained_elapsed")]),
+            "sm_active_frac": float(r[hdr.index("sm__cycles_active.avg")]) / float(r[hdr.index("sm__cycles_elapsed.avg")]),
+            "issue_active_pct": float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])}
+    out["onchip_pipe"] = {"per_kernel": pipe, "note": "L1TEX data pipe: pct of peak over the launch; divide by sm_active_frac for the "
+                          "share while the SMs hold a CTA (~66 % for every class = the SpMV share of an iteration: saturated "
+                          "during the SpMV, DESIGN 3.1a)"}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "cluster_traffic.json"), "w"), indent=1)
 print(json.dumps({k: out[k] for k in ("dram_bytes_per_launch", "l2_bytes_per_launch")}))
