@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--max-iter", type=int, default=20000)
     ap.add_argument("--streams", type=int, default=3, help="contexts (streams) the e2e path deals its steps to")
-    ap.add_argument("--cpu-samples", type=int, default=8, help="bounded sample for cpu_baseline")
+    ap.add_argument("--cpu-samples", type=int, default=32, help="bounded sample for cpu_baseline (about 10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--distinct-shards", action="store_true", help="every rank draws its own plates (N > 1)")
