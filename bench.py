@@ -389,9 +389,15 @@ def run_b200(a):
         dt = time.perf_counter() - t0
         # the same samples from the timed GPU step against the CPU direct solve (north_star: <= 1e-8)
         u_gpu = packed.split_vertices(res0.u)
-        errs = [float(np.linalg.norm(u_gpu[i] - u_cpu[i]) / np.linalg.norm(u_cpu[i])) for i in range(len(jobs))]
-        line["parity"] = {"samples": len(jobs), "max_rel_l2_vs_cpu_direct_solve": max(errs), "tolerance": 1e-8,
-                          "ok": bool(max(errs) <= 1e-8)}
+        # samples the solver does NOT report as converged (FEAnalysis.calculate() returns False for them and the
+        # generator redraws the condition) are listed, not compared: there is no converged result to compare
+        conv = [i for i in range(len(jobs)) if int(res0.status[i]) == 0]
+        errs = [float(np.linalg.norm(u_gpu[i] - u_cpu[i]) / np.linalg.norm(u_cpu[i])) for i in conv]
+        not_conv = {int(i): float(np.linalg.norm(u_gpu[i] - u_cpu[i]) / np.linalg.norm(u_cpu[i]))
+                    for i in range(len(jobs)) if i not in conv and np.isfinite(u_gpu[i]).all()}
+        line["parity"] = {"samples": len(conv), "max_rel_l2_vs_cpu_direct_solve": max(errs) if errs else None, "tolerance": 1e-8,
+                          "ok": bool(errs and max(errs) <= 1e-8),
+                          "reported_not_converged": {"count": len(jobs) - len(conv), "rel_l2_vs_cpu_direct_solve": not_conv}}
         line["cpu_baseline"] = {"value": len(jobs) / dt, "unit": "solves/s", "cores": 1, "kind": "port",
                                 "host_cores_available": os.cpu_count(),
                                 "sample": "first %d plate-conditions of the workload, %.1f s, reference-faithful "
