@@ -138,3 +138,17 @@ def test_pack_layout():
     assert p.vtx_off.tolist() == [0, 2464, 4928] and p.cell_off[-1] == 2 * 4686
     assert p.conn.dtype == np.int32 and p.fixed.dtype == np.uint8 and p.cell_region.dtype == np.int8
     assert p.desc.n_samples == 2 and p.desc.nodes_per_cell == 3
+
+
+def test_every_context_option_is_documented_in_the_header():
+    """fea_ctx_set_int keys accepted by the library (csrc/fea_api.cu) are all described in include/fea_b200.h."""
+    import re
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    src = open(os.path.join(root, "fea_diffusion_b200", "csrc", "fea_api.cu")).read()
+    body = src[src.index("int fea_ctx_set_int("):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'strcmp\(key, "([a-z_]+)"\)', body))
+    assert {"pcg_path", "cluster_min", "cluster_halo_cap", "row_order"} <= keys
+    header = open(os.path.join(root, "include", "fea_b200.h")).read()
+    missing = [k for k in sorted(keys) if '"%s"' % k not in header]
+    assert not missing, missing
