@@ -6,7 +6,7 @@ of namanxkumar/fea-diffusion (the solve + displacement rasterisation behind
 importable; it is the ``fea-diffusion_b200`` package of the project layout.)
 """
 from ._capi import FeaError, load_library  # noqa: F401
-from .solver import Batch, BatchResult, Context, PackedBatch, Sample, pack  # noqa: F401
+from .solver import Batch, BatchResult, Context, PackedBatch, PackedConditions, Sample, pack  # noqa: F401
 from .host import ProblemSetup, read_mesh, stiffness_plane_strain  # noqa: F401
 
 __all__ = ["FeaError", "load_library", "Batch", "BatchResult", "Context", "PackedBatch", "Sample",

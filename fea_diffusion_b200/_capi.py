@@ -18,7 +18,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 EXPORTS = [
     "fea_version", "fea_ctx_create", "fea_ctx_create_prio", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
-    "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create", "fea_batch_assemble",
+    "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create",
+    "fea_batch_create_from_conditions", "fea_batch_get_setup", "fea_batch_get_materials", "fea_batch_rasterize_regions",
+    "fea_batch_classify", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
     "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
     "fea_batch_get_timed_launches",
@@ -42,6 +44,21 @@ class BatchDesc(C.Structure):
         ("vtx_off", C.c_void_p), ("cell_off", C.c_void_p), ("reg_off", C.c_void_p),
         ("xy", C.c_void_p), ("conn", C.c_void_p), ("cell_region", C.c_void_p),
         ("D", C.c_void_p), ("fixed", C.c_void_p), ("rhs", C.c_void_p),
+    ]
+
+
+class ConditionsDesc(C.Structure):
+    """fea_conditions_desc (include/fea_b200.h)."""
+    _fields_ = [
+        ("n_meshes", C.c_int32), ("n_samples", C.c_int32), ("nodes_per_cell", C.c_int32), ("reserved", C.c_int32),
+        ("mesh_vtx_off", C.c_void_p), ("mesh_cell_off", C.c_void_p), ("xy", C.c_void_p), ("conn", C.c_void_p),
+        ("sample_mesh", C.c_void_p),
+        ("vforce_off", C.c_void_p), ("vforce_tag", C.c_void_p), ("vforce_mag", C.c_void_p),
+        ("eforce_off", C.c_void_p), ("eforce_tag", C.c_void_p), ("eforce_mag", C.c_void_p),
+        ("vfix_off", C.c_void_p), ("vfix_tag", C.c_void_p),
+        ("efix_off", C.c_void_p), ("efix_tag", C.c_void_p),
+        ("mat_off", C.c_void_p), ("mat_E_nu", C.c_void_p), ("mat_coord_off", C.c_void_p), ("mat_coords", C.c_void_p),
+        ("default_E_nu", C.c_void_p),
     ]
 
 
@@ -100,6 +117,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_ctx_event_elapsed_ms": (C.c_int, [P, I32, I32, P]),
         "fea_ctx_kernel_launches": (C.c_int, [P, P]),
         "fea_batch_create": (C.c_int, [P, C.POINTER(BatchDesc), C.POINTER(P)]),
+        "fea_batch_create_from_conditions": (C.c_int, [P, C.POINTER(ConditionsDesc), C.POINTER(P)]),
+        "fea_batch_get_setup": (C.c_int, [P, P, P, P, P, P]),
+        "fea_batch_get_materials": (C.c_int, [P, P, P, P]),
+        "fea_batch_rasterize_regions": (C.c_int, [P, P, P]),
+        "fea_batch_classify": (C.c_int, [P, P, P]),
         "fea_batch_assemble": (C.c_int, [P]),
         "fea_batch_solve": (C.c_int, [P, F64, I32]),
         "fea_batch_rasterize": (C.c_int, [P, I32, P, F64]),

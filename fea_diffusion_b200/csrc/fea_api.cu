@@ -11,46 +11,14 @@
 
 using namespace fea;
 
-struct fea_ctx {
-  Ctx c;
-  cudaEvent_t ev_user[8] = {};
-  cudaEvent_t ev_join = nullptr;
-};
-struct fea_batch {
-  Batch b;
-  fea_ctx* owner = nullptr;
-};
-
 namespace {
-
-int fail(fea_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
-  if (ctx) {
-    char buf[512];
-    if (e != cudaSuccess)
-      snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
-    else
-      snprintf(buf, sizeof buf, "%s", what);
-    ctx->c.err = buf;
-  }
-  if (e != cudaSuccess) cudaGetLastError();  // clear sticky-less errors
-  return code;
-}
 
 #define CK(ctx, call)                                                        \
   do {                                                                       \
     cudaError_t e_ = (call);                                                 \
     if (e_ != cudaSuccess)                                                   \
-      return fail(ctx, e_ == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, #call, e_); \
+      return api_fail(ctx, e_ == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, #call, e_); \
   } while (0)
-
-template <class T>
-cudaError_t dalloc(Batch& b, T** p, int64_t n) {
-  *p = nullptr;
-  if (n <= 0) n = 1;
-  cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (size_t)n, b.ctx->stream);
-  if (e == cudaSuccess) b.allocs.push_back(*p);
-  return e;
-}
 
 __global__ void k_gather_i32(const int32_t* __restrict__ src, const int64_t* __restrict__ idx, int n,
                              int32_t* __restrict__ dst) {
@@ -67,7 +35,24 @@ __global__ void k_localize_conn(int64_t NC, int npc, const int64_t* __restrict__
   for (int a = 0; a < npc; ++a) out[c * npc + a] = (int32_t)(conn[c * npc + a] - vtx_off[s]);
 }
 
-void free_batch(fea_batch* hb) {
+}  // namespace
+
+namespace fea {
+
+int api_fail(fea_ctx* ctx, int code, const char* what, cudaError_t e) {
+  if (ctx) {
+    char buf[512];
+    if (e != cudaSuccess)
+      snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+      snprintf(buf, sizeof buf, "%s", what);
+    ctx->c.err = buf;
+  }
+  if (e != cudaSuccess) cudaGetLastError();  // clear sticky-less errors
+  return code;
+}
+
+void api_free_batch(fea_batch* hb) {
   if (!hb) return;
   Batch& b = hb->b;
   cudaSetDevice(b.ctx->device);
@@ -76,7 +61,91 @@ void free_batch(fea_batch* hb) {
   delete hb;
 }
 
-}  // namespace
+int api_batch_begin(fea_ctx* ctx, int32_t ns, int32_t npc, const int64_t* vtx_off, const int64_t* cell_off,
+                    const int32_t* reg_off, fea_batch** out) {
+  *out = nullptr;
+  if (ns <= 0 || ns > kMaxSamplesPerBatch) return api_fail(ctx, FEA_BAD_ARG, "n_samples out of range");
+  if (npc != 3 && npc != 4) return api_fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
+  if (vtx_off[0] != 0 || cell_off[0] != 0 || reg_off[0] != 0) return api_fail(ctx, FEA_BAD_ARG, "offset tables must start at 0");
+  for (int s = 0; s < ns; ++s)
+    if (vtx_off[s + 1] < vtx_off[s] || cell_off[s + 1] < cell_off[s] || reg_off[s + 1] < reg_off[s])
+      return api_fail(ctx, FEA_BAD_ARG, "offset tables must be non-decreasing");
+  if (vtx_off[ns] >= (1LL << 30) || cell_off[ns] >= (1LL << 29)) return api_fail(ctx, FEA_BAD_ARG, "batch too large for 32-bit indices");
+  cudaError_t e0 = cudaSetDevice(ctx->c.device);
+  if (e0 != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "cudaSetDevice", e0);
+  fea_batch* hb = new (std::nothrow) fea_batch();
+  if (!hb) return api_fail(ctx, FEA_OUT_OF_MEMORY, "host allocation");
+  hb->owner = ctx;
+  Batch& b = hb->b;
+  b.ctx = &ctx->c;
+  b.ns = ns;
+  b.npc = npc;
+  b.vtx_off.assign(vtx_off, vtx_off + ns + 1);
+  b.cell_off.assign(cell_off, cell_off + ns + 1);
+  b.reg_off.assign(reg_off, reg_off + ns + 1);
+  b.NV = b.vtx_off[ns];
+  b.NC = b.cell_off[ns];
+  b.NREG = b.reg_off[ns];
+  b.NBR = 0;
+  for (int s = 0; s < ns; ++s) {
+    const int64_t nv = b.vtx_off[s + 1] - b.vtx_off[s];
+    const int64_t pad = (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
+    b.NBR += pad;
+    b.max_cta_count = std::max<int32_t>(b.max_cta_count, (int32_t)(pad / kCtaRows));  // upper bound
+  }
+  // on-chip solver path: every system is assigned a cluster class by its own size alone (the queue
+  // of a class is ordered on the device, launch_cluster_order)
+  int32_t n = 0;
+  for (int cls = 1; cls <= 8; ++cls) {
+    b.cl_off[cls] = n;
+    for (int s = 0; s < ns; ++s)
+      if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s], ctx->c.cluster_min) == cls) ++n;
+    b.cl_cnt[cls] = n - b.cl_off[cls];
+  }
+  *out = hb;
+  return FEA_OK;
+}
+
+cudaError_t api_batch_finish(Batch& b, const int8_t* creg_local, const int32_t* conn_local) {
+  cudaStream_t st = b.ctx->stream;
+  const int ns = b.ns;
+  cudaError_t e = cudaSuccess;
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(dalloc(b, &b.conn, b.NC * b.npc));
+  A(dalloc(b, &b.cell_dreg, b.NC));
+  A(dalloc(b, &b.d_vtx_off, ns + 1));
+  A(dalloc(b, &b.d_cell_off, ns + 1));
+  A(dalloc(b, &b.d_reg_off, ns + 1));
+  A(dalloc(b, &b.vsample, b.NV));
+  A(dalloc(b, &b.flips, ns));
+  A(dalloc(b, &b.vrank, b.NV));
+  A(dalloc(b, &b.prank, b.NV));
+  A(dalloc(b, &b.n_active, ns));
+  A(dalloc(b, &b.row_base, ns + 1));
+  A(dalloc(b, &b.row_of_vertex, b.NV));
+  A(dalloc(b, &b.vertex_of_row, b.NBR));
+  A(dalloc(b, &b.sys_of_cta, b.NBR / kCtaRows));
+  A(dalloc(b, &b.cta_first, ns));
+  A(dalloc(b, &b.cta_count, ns));
+  A(dalloc(b, &b.err_flag, 4));
+  A(dalloc(b, &b.empty, ns));
+  A(dalloc(b, &b.cl_order, ns));
+  A(dalloc(b, &b.cl_counter, 16));  // queue heads of the cluster classes, restart count, scratch
+  A(cudaMemcpyAsync(b.d_vtx_off, b.vtx_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.d_cell_off, b.cell_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(b.d_reg_off, b.reg_off.data(), sizeof(int32_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+  A(cudaMemsetAsync(b.flips, 0, sizeof(int32_t) * ns, st));
+  A(cudaMemsetAsync(b.err_flag, 0, sizeof(int32_t) * 4, st));
+  A(cudaMemsetAsync(b.empty, 0, sizeof(int32_t) * ns, st));
+  A(cudaMemsetAsync(b.vertex_of_row, 0xFF, sizeof(int32_t) * std::max<int64_t>(1, b.NBR), st));
+  A(launch_setup(b, creg_local, conn_local));
+  A(launch_cluster_order(b));
+#undef A
+  b.ctx->launches += 7;
+  return e;
+}
+
+}  // namespace fea
 
 extern "C" {
 
@@ -204,7 +273,7 @@ int fea_ctx_event_elapsed_ms(fea_ctx* ctx, int32_t a, int32_t b, float* ms) {
 int fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other) {
   if (!ctx || !other) return FEA_BAD_ARG;
   if (ctx == other) return FEA_OK;
-  if (ctx->c.device != other->c.device) return fail(ctx, FEA_BAD_ARG, "contexts are on different devices");
+  if (ctx->c.device != other->c.device) return api_fail(ctx, FEA_BAD_ARG, "contexts are on different devices");
   CK(ctx, cudaSetDevice(ctx->c.device));
   CK(ctx, cudaEventRecord(other->ev_join, other->c.stream));
   CK(ctx, cudaStreamWaitEvent(ctx->c.stream, other->ev_join, 0));
@@ -219,7 +288,7 @@ int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
   else if (strcmp(key, "refine_rounds") == 0) ctx->c.refine_rounds = value < 0 ? 0 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;
   else if (strcmp(key, "use_graphs") == 0) ctx->c.use_graphs = value ? 1 : 0;
-  else return fail(ctx, FEA_BAD_ARG, "unknown option key");
+  else return api_fail(ctx, FEA_BAD_ARG, "unknown option key");
   return FEA_OK;
 }
 int fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out) {
@@ -232,88 +301,21 @@ int fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out) {
 int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   if (!ctx || !d || !out) return FEA_BAD_ARG;
   *out = nullptr;
-  if (d->n_samples <= 0 || d->n_samples > kMaxSamplesPerBatch) return fail(ctx, FEA_BAD_ARG, "n_samples out of range");
-  if (d->nodes_per_cell != 3 && d->nodes_per_cell != 4) return fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
   if (!d->vtx_off || !d->cell_off || !d->reg_off || !d->xy || !d->conn || !d->cell_region || !d->D || !d->fixed || !d->rhs)
-    return fail(ctx, FEA_BAD_ARG, "null array in fea_batch_desc");
-  const int ns = d->n_samples;
-  if (d->vtx_off[0] != 0 || d->cell_off[0] != 0 || d->reg_off[0] != 0) return fail(ctx, FEA_BAD_ARG, "offset tables must start at 0");
-  for (int s = 0; s < ns; ++s)
-    if (d->vtx_off[s + 1] < d->vtx_off[s] || d->cell_off[s + 1] < d->cell_off[s] || d->reg_off[s + 1] < d->reg_off[s])
-      return fail(ctx, FEA_BAD_ARG, "offset tables must be non-decreasing");
-  if (d->vtx_off[ns] >= (1LL << 30) || d->cell_off[ns] >= (1LL << 29)) return fail(ctx, FEA_BAD_ARG, "batch too large for 32-bit indices");
-  CK(ctx, cudaSetDevice(ctx->c.device));
-  fea_batch* hb = new (std::nothrow) fea_batch();
-  if (!hb) return fail(ctx, FEA_OUT_OF_MEMORY, "host allocation");
-  hb->owner = ctx;
+    return api_fail(ctx, FEA_BAD_ARG, "null array in fea_batch_desc");
+  fea_batch* hb = nullptr;
+  int rc = api_batch_begin(ctx, d->n_samples, d->nodes_per_cell, d->vtx_off, d->cell_off, d->reg_off, &hb);
+  if (rc != FEA_OK) return rc;
   Batch& b = hb->b;
-  b.ctx = &ctx->c;
-  b.ns = ns;
-  b.npc = d->nodes_per_cell;
-  b.vtx_off.assign(d->vtx_off, d->vtx_off + ns + 1);
-  b.cell_off.assign(d->cell_off, d->cell_off + ns + 1);
-  b.reg_off.assign(d->reg_off, d->reg_off + ns + 1);
-  b.NV = b.vtx_off[ns];
-  b.NC = b.cell_off[ns];
-  b.NREG = b.reg_off[ns];
-  b.NBR = 0;
-  for (int s = 0; s < ns; ++s) {
-    const int64_t nv = b.vtx_off[s + 1] - b.vtx_off[s];
-    const int64_t pad = (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
-    b.NBR += pad;
-    b.max_cta_count = std::max<int32_t>(b.max_cta_count, (int32_t)(pad / kCtaRows));  // upper bound
-  }
-  // on-chip solver path: every system is assigned a cluster class by its own size alone.  Inside a
-  // class the queue is ordered longest-job-first by an estimate of the work, rows x iterations: the
-  // iteration count of Jacobi-PCG on these plates falls with the number of constrained vertices
-  // (measured on 800 bench samples: iters ~ 2560 - 344 ln(n_fixed), R^2 0.44), and starting the
-  // long solves first shortens the tail of a batch by 15-20 %.  The order only decides WHEN a
-  // system is solved, never its bits.
-  std::vector<int32_t> order;
-  std::vector<double> work(ns, 0.0);
-  for (int s = 0; s < ns; ++s) {
-    int64_t nfix = 0;
-    for (int64_t v = b.vtx_off[s]; v < b.vtx_off[s + 1]; ++v) nfix += d->fixed[v] != 0;
-    const double it = std::max(100.0, 2560.0 - 344.0 * std::log((double)std::max<int64_t>(nfix, 1)));
-    work[s] = it * (double)(b.vtx_off[s + 1] - b.vtx_off[s] - nfix);
-  }
-  for (int cls = 1; cls <= 8; ++cls) {
-    b.cl_off[cls] = (int32_t)order.size();
-    for (int s = 0; s < ns; ++s)
-      if (pcg_cluster_class(b.vtx_off[s + 1] - b.vtx_off[s], ctx->c.cluster_min) == cls) order.push_back(s);
-    b.cl_cnt[cls] = (int32_t)order.size() - b.cl_off[cls];
-    std::stable_sort(order.begin() + b.cl_off[cls], order.end(), [&](int32_t x, int32_t y) { return work[x] > work[y]; });
-  }
   cudaStream_t st = ctx->c.stream;
   int32_t* conn_local = nullptr;
   int8_t* creg_local = nullptr;
   cudaError_t e = cudaSuccess;
 #define A(call) if (e == cudaSuccess) e = (call)
   A(dalloc(b, &b.xy, b.NV * 2));
-  A(dalloc(b, &b.conn, b.NC * b.npc));
-  A(dalloc(b, &b.cell_dreg, b.NC));
   A(dalloc(b, &b.D, (int64_t)b.NREG * 9));
   A(dalloc(b, &b.fixed, b.NV));
   A(dalloc(b, &b.rhs, b.NV * 2));
-  A(dalloc(b, &b.d_vtx_off, ns + 1));
-  A(dalloc(b, &b.d_cell_off, ns + 1));
-  A(dalloc(b, &b.d_reg_off, ns + 1));
-  A(dalloc(b, &b.vsample, b.NV));
-  A(dalloc(b, &b.flips, ns));
-  A(dalloc(b, &b.vrank, b.NV));
-  A(dalloc(b, &b.prank, b.NV));
-  A(dalloc(b, &b.n_active, ns));
-  A(dalloc(b, &b.row_base, ns + 1));
-  A(dalloc(b, &b.row_of_vertex, b.NV));
-  A(dalloc(b, &b.vertex_of_row, b.NBR));
-  A(dalloc(b, &b.sys_of_cta, b.NBR / kCtaRows));
-  A(dalloc(b, &b.cta_first, ns));
-  A(dalloc(b, &b.cta_count, ns));
-  A(dalloc(b, &b.err_flag, 4));
-  A(dalloc(b, &b.empty, ns));
-  A(dalloc(b, &b.cl_order, ns));
-  A(dalloc(b, &b.cl_counter, 16));  // queue heads of the cluster classes, restart count, scratch
-  if (!order.empty()) A(cudaMemcpyAsync(b.cl_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
   A(cudaMallocAsync((void**)&conn_local, sizeof(int32_t) * std::max<int64_t>(1, b.NC * b.npc), st));
   A(cudaMallocAsync((void**)&creg_local, std::max<int64_t>(1, b.NC), st));
   A(cudaMemcpyAsync(b.xy, d->xy, sizeof(double) * b.NV * 2, cudaMemcpyHostToDevice, st));
@@ -322,21 +324,13 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
   A(cudaMemcpyAsync(b.D, d->D, sizeof(double) * 9 * b.NREG, cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(b.fixed, d->fixed, b.NV, cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(b.rhs, d->rhs, sizeof(double) * b.NV * 2, cudaMemcpyHostToDevice, st));
-  A(cudaMemcpyAsync(b.d_vtx_off, b.vtx_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
-  A(cudaMemcpyAsync(b.d_cell_off, b.cell_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
-  A(cudaMemcpyAsync(b.d_reg_off, b.reg_off.data(), sizeof(int32_t) * (ns + 1), cudaMemcpyHostToDevice, st));
-  A(cudaMemsetAsync(b.flips, 0, sizeof(int32_t) * ns, st));
-  A(cudaMemsetAsync(b.err_flag, 0, sizeof(int32_t) * 4, st));
-  A(cudaMemsetAsync(b.empty, 0, sizeof(int32_t) * ns, st));
-  A(cudaMemsetAsync(b.vertex_of_row, 0xFF, sizeof(int32_t) * std::max<int64_t>(1, b.NBR), st));
-  A(launch_setup(b, creg_local, conn_local));
-  ctx->c.launches += 6;
+  A(api_batch_finish(b, creg_local, conn_local));
   if (conn_local) cudaFreeAsync(conn_local, st);
   if (creg_local) cudaFreeAsync(creg_local, st);
 #undef A
   if (e != cudaSuccess) {
-    int rc = fail(ctx, e == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, "fea_batch_create", e);
-    free_batch(hb);
+    rc = api_fail(ctx, e == cudaErrorMemoryAllocation ? FEA_OUT_OF_MEMORY : FEA_CUDA_ERROR, "fea_batch_create", e);
+    api_free_batch(hb);
     return rc;
   }
   *out = hb;
@@ -345,7 +339,7 @@ int fea_batch_create(fea_ctx* ctx, const fea_batch_desc* d, fea_batch** out) {
 
 int fea_batch_destroy(fea_batch* hb) {
   if (!hb) return FEA_OK;
-  free_batch(hb);
+  api_free_batch(hb);
   return FEA_OK;
 }
 
@@ -368,14 +362,15 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, launch_topology_counts(b));
   CK(ctx, launch_sell_lengths(b));
   // one host round trip: totals and error flags
-  int32_t h_adj = 0, h_err[2] = {0, 0};
+  int32_t h_adj = 0, h_err[3] = {0, 0, 0};
   int64_t h_blocks = 0;
   CK(ctx, cudaMemcpyAsync(&h_adj, b.adj_ptr + b.NV, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaMemcpyAsync(&h_blocks, b.slice_ptr + b.n_slices, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(h_err, b.err_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(h_err, b.err_flag, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
-  if (h_err[0] & 2) return fail(ctx, FEA_MESH_ERROR, "connectivity or cell_region index out of range");
-  if (h_err[0] & 1) return fail(ctx, FEA_MESH_ERROR, "vertex valence exceeds the supported maximum (63)");
+  if (h_err[0] & 2) return api_fail(ctx, FEA_MESH_ERROR, "connectivity or cell_region index out of range");
+  if (h_err[0] & 1) return api_fail(ctx, FEA_MESH_ERROR, "vertex valence exceeds the supported maximum (63)");
+  if (h_err[2] & 4) return api_fail(ctx, FEA_MESH_ERROR, "more than 16 distinct overlap combinations of material regions in one sample");
   b.n_adj = h_adj;
   b.n_blocks = b.n_slices ? h_blocks : 0;
   b.max_row_blocks = h_err[1];
@@ -422,8 +417,8 @@ int fea_batch_solve(fea_batch* hb, double rtol, int32_t max_iter) {
   if (!hb) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_solve before fea_batch_assemble");
-  if (!(rtol >= 0.0) || max_iter < 1) return fail(ctx, FEA_BAD_ARG, "rtol must be >= 0 and max_iter >= 1");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_solve before fea_batch_assemble");
+  if (!(rtol >= 0.0) || max_iter < 1) return api_fail(ctx, FEA_BAD_ARG, "rtol must be >= 0 and max_iter >= 1");
   CK(ctx, cudaSetDevice(ctx->c.device));
   CK(ctx, run_pcg(b, rtol, max_iter));
   b.solved = true;
@@ -434,8 +429,8 @@ int fea_batch_rasterize(fea_batch* hb, int32_t size, const double* affine, doubl
   if (!hb || !affine) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize before fea_batch_solve");
-  if (size < 1 || size > 8192) return fail(ctx, FEA_BAD_ARG, "image size out of range");
+  if (!b.solved) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize before fea_batch_solve");
+  if (size < 1 || size > 8192) return api_fail(ctx, FEA_BAD_ARG, "image size out of range");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   if (b.img_size != size) {
@@ -456,7 +451,7 @@ int fea_batch_download(fea_batch* hb, double* u, double* ranges, int32_t* iters,
   if (!hb) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_download before fea_batch_solve");
+  if (!b.solved) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_download before fea_batch_solve");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   if (u) CK(ctx, cudaMemcpyAsync(u, b.u, sizeof(double) * 2 * b.NV, cudaMemcpyDeviceToHost, st));
@@ -472,11 +467,11 @@ int fea_batch_rasterize_flags(fea_batch* hb, const int64_t* field_off, const uin
   if (!hb || !field_off || !flags || !images) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.rasterized) return fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize_flags before fea_batch_rasterize");
-  if (field_off[0] != 0) return fail(ctx, FEA_BAD_ARG, "field_off must start at 0");
+  if (!b.rasterized) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize_flags before fea_batch_rasterize");
+  if (field_off[0] != 0) return api_fail(ctx, FEA_BAD_ARG, "field_off must start at 0");
   std::vector<int64_t> flag_off(b.ns + 1, 0);
   for (int s = 0; s < b.ns; ++s) {
-    if (field_off[s + 1] < field_off[s]) return fail(ctx, FEA_BAD_ARG, "field_off must be non-decreasing");
+    if (field_off[s + 1] < field_off[s]) return api_fail(ctx, FEA_BAD_ARG, "field_off must be non-decreasing");
     flag_off[s + 1] = flag_off[s] + (field_off[s + 1] - field_off[s]) * (b.vtx_off[s + 1] - b.vtx_off[s]);
   }
   const int64_t n_img = field_off[b.ns], n_flags = flag_off[b.ns];
@@ -497,7 +492,7 @@ int fea_batch_rasterize_flags(fea_batch* hb, const int64_t* field_off, const uin
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // flag_off (host vector) must outlive the copy
   cudaFreeAsync(d, st);
   ctx->c.launches += 1;
-  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_rasterize_flags", e);
+  if (e != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "fea_batch_rasterize_flags", e);
   return FEA_OK;
 }
 
@@ -505,7 +500,7 @@ int fea_batch_cell_strain_stress(fea_batch* hb, int32_t stress_region, double* s
   if (!hb || (!strain && !stress)) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.solved) return fail(ctx, FEA_BAD_STATE, "fea_batch_cell_strain_stress before fea_batch_solve");
+  if (!b.solved) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_cell_strain_stress before fea_batch_solve");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   double* d = nullptr;
@@ -517,7 +512,7 @@ int fea_batch_cell_strain_stress(fea_batch* hb, int32_t stress_region, double* s
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFreeAsync(d, st);
   ctx->c.launches += 1;
-  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_batch_cell_strain_stress", e);
+  if (e != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "fea_batch_cell_strain_stress", e);
   return FEA_OK;
 }
 
@@ -525,7 +520,7 @@ int fea_batch_download_images(fea_batch* hb, uint8_t* images) {
   if (!hb || !images) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.rasterized) return fail(ctx, FEA_BAD_STATE, "fea_batch_download_images before fea_batch_rasterize");
+  if (!b.rasterized) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_download_images before fea_batch_rasterize");
   CK(ctx, cudaSetDevice(ctx->c.device));
   CK(ctx, cudaMemcpyAsync(images, b.images, (size_t)b.ns * 2 * b.img_size * b.img_size, cudaMemcpyDeviceToHost, ctx->c.stream));
   CK(ctx, cudaStreamSynchronize(ctx->c.stream));
@@ -536,7 +531,7 @@ int fea_batch_sample_sizes(fea_batch* hb, int64_t* n_active_dofs, int64_t* nnz) 
   if (!hb) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_sample_sizes before fea_batch_assemble");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_sample_sizes before fea_batch_assemble");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   std::vector<int32_t> na(b.ns), ap(b.ns + 1);
@@ -558,7 +553,7 @@ int fea_batch_get_info(fea_batch* hb, fea_batch_info* out) {
   if (!hb || !out) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_get_info before fea_batch_assemble");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_get_info before fea_batch_assemble");
   CK(ctx, cudaSetDevice(ctx->c.device));
   std::vector<int32_t> na(b.ns), fl(b.ns);
   int64_t rows = 0;
@@ -623,7 +618,7 @@ int fea_batch_get_element_stiffness(fea_batch* hb, double* ke) {
   if (!hb || !ke) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "element stiffness requested before fea_batch_assemble");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "element stiffness requested before fea_batch_assemble");
   CK(ctx, cudaSetDevice(ctx->c.device));
   const int N = 2 * b.npc;
   CK(ctx, cudaMemcpyAsync(ke, b.ke, sizeof(double) * b.NC * N * N, cudaMemcpyDeviceToHost, ctx->c.stream));
@@ -635,8 +630,8 @@ int fea_batch_get_csr(fea_batch* hb, int32_t s, int32_t* indptr, int32_t* indice
   if (!hb) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_get_csr before fea_batch_assemble");
-  if (s < 0 || s >= b.ns) return fail(ctx, FEA_BAD_ARG, "sample index out of range");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_get_csr before fea_batch_assemble");
+  if (s < 0 || s >= b.ns) return api_fail(ctx, FEA_BAD_ARG, "sample index out of range");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   int32_t na = 0, a0 = 0, a1 = 0;
@@ -668,8 +663,8 @@ int fea_batch_spmv(fea_batch* hb, int32_t s, const double* x, double* y) {
   if (!hb || !x || !y) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;
   Batch& b = hb->b;
-  if (!b.assembled) return fail(ctx, FEA_BAD_STATE, "fea_batch_spmv before fea_batch_assemble");
-  if (s < 0 || s >= b.ns) return fail(ctx, FEA_BAD_ARG, "sample index out of range");
+  if (!b.assembled) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_spmv before fea_batch_assemble");
+  if (s < 0 || s >= b.ns) return api_fail(ctx, FEA_BAD_ARG, "sample index out of range");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   int32_t na = 0;
@@ -693,12 +688,12 @@ int fea_rasterize_fields(fea_ctx* ctx, const double* xy, int64_t n_v, const int3
                          int32_t nodes_per_cell, const double* fields, int32_t n_fields, int32_t cell_fields,
                          const double* clim, const double* affine, int32_t size, uint8_t* images) {
   if (!ctx) return FEA_BAD_ARG;
-  if (!xy || !conn || !fields || !clim || !affine || !images) return fail(ctx, FEA_BAD_ARG, "null array");
-  if (nodes_per_cell != 3 && nodes_per_cell != 4) return fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
+  if (!xy || !conn || !fields || !clim || !affine || !images) return api_fail(ctx, FEA_BAD_ARG, "null array");
+  if (nodes_per_cell != 3 && nodes_per_cell != 4) return api_fail(ctx, FEA_BAD_ARG, "nodes_per_cell must be 3 or 4");
   if (n_v < 1 || n_cell < 0 || n_fields < 1 || size < 1 || size > 8192 || n_v >= (1LL << 30))
-    return fail(ctx, FEA_BAD_ARG, "size out of range");
+    return api_fail(ctx, FEA_BAD_ARG, "size out of range");
   for (int64_t i = 0; i < n_cell * nodes_per_cell; ++i)
-    if (conn[i] < 0 || conn[i] >= n_v) return fail(ctx, FEA_MESH_ERROR, "connectivity index out of range");
+    if (conn[i] < 0 || conn[i] >= n_v) return api_fail(ctx, FEA_MESH_ERROR, "connectivity index out of range");
   CK(ctx, cudaSetDevice(ctx->c.device));
   cudaStream_t st = ctx->c.stream;
   const int64_t per = (int64_t)size * size;
@@ -726,7 +721,7 @@ int fea_rasterize_fields(fea_ctx* ctx, const double* xy, int64_t n_v, const int3
 #undef A
   cudaFreeAsync(d, st);
   ctx->c.launches += 3;
-  if (e != cudaSuccess) return fail(ctx, FEA_CUDA_ERROR, "fea_rasterize_fields", e);
+  if (e != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "fea_rasterize_fields", e);
   return FEA_OK;
 }
 

@@ -137,11 +137,60 @@ struct Batch {
   double* affine = nullptr;  // [ns*4]
   fea_solve_stats stats{};
   std::vector<float> t_spmv, t_update;  // per timed launch (one per chunk)
+  // ---- set-up derived on the device from tags / magnitudes / coordinate lists
+  //      (fea_batch_create_from_conditions, k_conditions.cu) ----
+  bool from_conditions = false;
+  int64_t NR = 0;                  // regions of all samples
+  std::vector<int32_t> sreg_off;   // [ns+1] first region of each sample
+  std::vector<int64_t> flag_off;   // [ns+1] offset of each sample's flag block: (n_regions + 1) rows of n_v
+                                   // bytes, the extra last row is all ones (the plate mask of input.png)
+  uint8_t* rflags = nullptr;       // region vertex flags
+  int32_t* rcount = nullptr;       // [NR] vertices per region
+  int8_t* creg_local = nullptr;    // [NC] sample-local material-table index of each cell, -1 = none
+  int32_t* n_reg_used = nullptr;   // [ns] material-table entries in use (terms + overlap combinations)
 };
+
+}  // namespace fea
+
+// the opaque handles of the C-ABI
+struct fea_ctx {
+  fea::Ctx c;
+  cudaEvent_t ev_user[8] = {};
+  cudaEvent_t ev_join = nullptr;
+};
+struct fea_batch {
+  fea::Batch b;
+  fea_ctx* owner = nullptr;
+};
+
+namespace fea {
+
+// error bookkeeping shared by the API translation units (fea_api.cu)
+int api_fail(fea_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess);
+void api_free_batch(fea_batch* hb);
+// host-side part of batch creation that does not depend on how the set-up arrays were produced:
+// sizes, offset tables, cluster classes.  Returns FEA_OK or a status (message set on ctx).
+int api_batch_begin(fea_ctx* ctx, int32_t ns, int32_t npc, const int64_t* vtx_off, const int64_t* cell_off,
+                    const int32_t* reg_off, fea_batch** out);
+// allocations of the arrays launch_setup fills, offset-table uploads, launch_setup itself and the
+// device-side ordering of the cluster queues; b.xy, b.D, b.fixed, b.rhs must be allocated and
+// (stream-ordered) filled, conn_local / creg_local are consumed.
+cudaError_t api_batch_finish(Batch& b, const int8_t* d_creg_local, const int32_t* d_conn_local);
+
+template <class T>
+inline cudaError_t dalloc(Batch& b, T** p, int64_t n) {
+  *p = nullptr;
+  if (n <= 0) n = 1;
+  cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (size_t)n, b.ctx->stream);
+  if (e == cudaSuccess) b.allocs.push_back(*p);
+  return e;
+}
 
 // ---- launchers implemented in the kernel translation units -----------------
 // All return cudaError_t of the launch (cudaGetLastError).
 cudaError_t launch_setup(Batch& b, const int8_t* d_cell_region_local, const int32_t* d_conn_local);
+cudaError_t launch_cluster_order(Batch& b);                   // longest-job-first queues of the on-chip classes
+cudaError_t launch_classify(Batch& b, int32_t* d_floating, int32_t* d_empty);   // A-19, needs the incidence lists
 cudaError_t launch_topology_counts(Batch& b);                 // incidence + adjacency counts
 cudaError_t launch_topology_fill(Batch& b);                   // adjacency fill
 cudaError_t launch_element_stiffness(Batch& b);
@@ -154,7 +203,8 @@ cudaError_t launch_csr_export(Batch& b, int32_t s, int32_t* d_indptr, int32_t* d
 cudaError_t run_pcg(Batch& b, double rtol, int max_iter);
 void pcg_release(Ctx& c);                                     // destroys the cached graphs
 int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl);  // CTAs per cluster (1..8), 0: streaming
-int pcg_cluster_capacity(Ctx& c, int cl);                     // co-resident clusters (0 = unavailable)
+int pcg_cluster_capacity(Ctx& c, int cl);
+int pcg_cluster_rows_per_cta();                               // block rows a CTA of the on-chip path holds                     // co-resident clusters (0 = unavailable)
 struct PcgPtrs;
 cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st);
 cudaError_t launch_finalize(Batch& b);                        // u, ranges, max-iter status

@@ -769,6 +769,8 @@ int pcg_cluster_class(int64_t n_vertices_of_sample, int min_cl) {
   return cl <= kClMax ? (int)cl : 0;
 }
 
+int pcg_cluster_rows_per_cta() { return kClSlices * 32; }
+
 cudaError_t launch_pcg_cluster(Ctx& c, const PcgPtrs* dP, int n_systems, int cl, cudaStream_t st) {
   const int capn = pcg_cluster_capacity(c, cl);
   if (capn <= 0 || n_systems <= 0) return cudaSuccess;

@@ -368,6 +368,67 @@ __global__ void __launch_bounds__(kSortThreads) k_spatial_rank(const int64_t* __
     if (vrank[v0 + i] < 0) prank[v0 + i] = -1;
 }
 
+// ---------------------------------------------------------------------------
+// Queues of the on-chip solver classes (k_pcg_cluster): inside a class the systems are ordered
+// longest-job-first by an estimate of the work, rows x iterations.  The iteration count of
+// Jacobi-PCG on these plates falls with the number of constrained vertices (measured on 800 bench
+// samples: iters ~ 2560 - 344 ln(n_fixed), R^2 0.44), and starting the long solves first shortens
+// the tail of a batch by 15-20 %.  The order only decides WHEN a system is solved, never its bits.
+// One CTA: 64-bit keys (class | inverted work | system) sorted by a bitonic network in global
+// memory (L2 resident; a batch has at most 2^20 systems).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_cluster_order(int ns, int n2, const int64_t* __restrict__ vtx_off,
+                                                        const int32_t* __restrict__ n_active, int rows_per_cta,
+                                                        int min_cl, int max_cl, unsigned long long* __restrict__ keys,
+                                                        int n_out, int32_t* __restrict__ cl_order) {
+  for (int s = threadIdx.x; s < n2; s += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (s < ns) {
+      const int64_t nv = vtx_off[s + 1] - vtx_off[s];
+      const int64_t pad = (nv + kCtaRows - 1) / kCtaRows * kCtaRows;
+      int64_t cl = pad > 0 ? (pad + rows_per_cta - 1) / rows_per_cta : 0;
+      if (cl > 0 && cl < min_cl) cl = min_cl;
+      if (cl >= 1 && cl <= max_cl) {
+        const int na = n_active[s];
+        const int64_t nfix = nv - na;
+        const double it = fmax(100.0, 2560.0 - 344.0 * log((double)(nfix > 1 ? nfix : 1)));
+        const double work = fmin(it * (double)na, 268435455.0);
+        k = ((unsigned long long)cl << 60) | ((unsigned long long)(268435455u - (unsigned)work) << 32) | (unsigned)s;
+      }
+    }
+    keys[s] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) cl_order[i] = (int32_t)(keys[i] & 0xffffffffu);
+}
+
+cudaError_t launch_cluster_order(Batch& b) {
+  cudaStream_t st = b.ctx->stream;
+  const int n_out = b.cl_off[8] + b.cl_cnt[8];
+  if (n_out == 0) return cudaSuccess;
+  int n2 = 2;
+  while (n2 < b.ns) n2 <<= 1;
+  unsigned long long* keys = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&keys, sizeof(unsigned long long) * n2, st);
+  if (e != cudaSuccess) return e;
+  k_cluster_order<<<1, 1024, 0, st>>>(b.ns, n2, b.d_vtx_off, b.n_active, pcg_cluster_rows_per_cta(), b.ctx->cluster_min, 8,
+                                      keys, n_out, b.cl_order);
+  cudaFreeAsync(keys, st);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_setup(Batch& b, const int8_t* d_creg_local, const int32_t* d_conn_local) {
   cudaStream_t st = b.ctx->stream;
   const int T = 256;

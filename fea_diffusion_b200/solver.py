@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _capi
-from ._capi import BatchDesc, BatchInfo, FeaError, SolveStats, ptr
+from ._capi import BatchDesc, BatchInfo, ConditionsDesc, FeaError, SolveStats, ptr
 
 
 @dataclass
@@ -71,12 +71,146 @@ class PackedBatch:
         return int(self.vtx_off[-1])
 
     @property
+    def n_cells(self) -> int:
+        return int(self.cell_off[-1])
+
+    @property
     def h2d_bytes(self) -> int:
         return int(sum(a.nbytes for a in (self.vtx_off, self.cell_off, self.reg_off, self.xy, self.conn,
                                           self.cell_region, self.D, self.fixed, self.rhs)))
 
     def split_vertices(self, a: np.ndarray) -> List[np.ndarray]:
         return [a[self.vtx_off[s]:self.vtx_off[s + 1]] for s in range(self.n)]
+
+
+class PackedConditions:
+    """Plate-conditions in the reference's own terms -- tags, magnitudes and material coordinate
+    lists, the keyword arguments of ``FEAnalysis.__init__`` (reference fea_analysis.py:32-48) -- packed
+    into the flat arrays of ``fea_conditions_desc``.  Region selection, Dirichlet mask, material
+    cells, D and the load vector are then derived on the device
+    (``Context.create_batch_from_conditions``).
+
+    ``meshes``: sequence of (coors (n_v, 2), conn (n_cell, k)); ``samples``: sequence of
+    (mesh index, kwargs) with kwargs as produced by ``plates.condition_kwargs``.
+    """
+
+    KINDS = ("VertexForce", "EdgeForce", "VertexConstraint", "EdgeConstraint", "MaterialRegion")
+
+    def __init__(self, meshes: Sequence, samples: Sequence, alloc=None):
+        if not meshes or not samples:
+            raise ValueError("empty batch")
+        k = np.asarray(meshes[0][1]).shape[1]
+        self.k, self.n, self.n_meshes = k, len(samples), len(meshes)
+        A = (lambda shape, dtype: np.empty(shape, dtype)) if alloc is None else alloc
+
+        def cat(parts, dtype, width):
+            total = sum(len(p) for p in parts)
+            out = A((total, width) if width else (total,), dtype)
+            o = 0
+            for p in parts:
+                out[o:o + len(p)] = p
+                o += len(p)
+            return out
+
+        mv = np.array([len(m[0]) for m in meshes], dtype=np.int64)
+        mc = np.array([len(m[1]) for m in meshes], dtype=np.int64)
+        self.mesh_vtx_off = np.concatenate([[0], np.cumsum(mv)]).astype(np.int64)
+        self.mesh_cell_off = np.concatenate([[0], np.cumsum(mc)]).astype(np.int64)
+        self.xy = cat([np.asarray(m[0], dtype=np.float64).reshape(-1, 2) for m in meshes], np.float64, 2)
+        self.conn = cat([np.asarray(m[1], dtype=np.int32).reshape(-1, k) for m in meshes], np.int32, k)
+        self.sample_mesh = np.array([int(m) for m, _ in samples], dtype=np.int32)
+        vf_t, vf_m, ef_t, ef_m, vc_t, ec_t, mat_en, mat_xy, dflt = [], [], [], [], [], [], [], [], []
+        n_vf, n_ef, n_vc, n_ec, n_mat = [], [], [], [], []
+        self.names: List[List[str]] = []
+        self.materials: List[List] = []
+        for _, kw in samples:
+            vf = kw.get("force_vertex_tags_magnitudes") or ()
+            ef = kw.get("force_edges_tags_magnitudes") or ()
+            vc = kw.get("constraints_vertex_tags") or ()
+            ec = kw.get("constraints_edges_tags") or ()
+            mats = kw.get("material_properties_to_vertices")
+            items = list(mats.items()) if mats is not None else []
+            vf_t.extend(int(t) for t, _ in vf)
+            vf_m.extend((float(m[0]), float(m[1])) for _, m in vf)
+            ef_t.extend((int(t[0]), int(t[1])) for t, _ in ef)
+            ef_m.extend((float(m[0]), float(m[1])) for _, m in ef)
+            vc_t.extend(int(t) for t in vc)
+            ec_t.extend((int(t[0]), int(t[1])) for t in ec)
+            for (E, nu), pts in items:
+                mat_en.append((float(E), float(nu)))
+                mat_xy.append(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
+            dflt.append((float(kw.get("youngs_modulus", 210000)), float(kw.get("poisson_ratio", 0.3))))
+            n_vf.append(len(vf)); n_ef.append(len(ef)); n_vc.append(len(vc)); n_ec.append(len(ec)); n_mat.append(len(items))
+            self.names.append(["%s%d" % (kind, i) for kind, cnt in zip(self.KINDS, (len(vf), len(ef), len(vc), len(ec), len(items)))
+                               for i in range(cnt)])
+            self.materials.append([key for key, _ in items])
+
+        def offs(counts):
+            return np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+
+        self.vforce_off, self.eforce_off, self.vfix_off = offs(n_vf), offs(n_ef), offs(n_vc)
+        self.efix_off, self.mat_off = offs(n_ec), offs(n_mat)
+        self.vforce_tag = np.asarray(vf_t, dtype=np.int32).reshape(-1)
+        self.vforce_mag = np.asarray(vf_m, dtype=np.float64).reshape(-1, 2)
+        self.eforce_tag = np.asarray(ef_t, dtype=np.int32).reshape(-1, 2)
+        self.eforce_mag = np.asarray(ef_m, dtype=np.float64).reshape(-1, 2)
+        self.vfix_tag = np.asarray(vc_t, dtype=np.int32).reshape(-1)
+        self.efix_tag = np.asarray(ec_t, dtype=np.int32).reshape(-1, 2)
+        self.mat_E_nu = np.asarray(mat_en, dtype=np.float64).reshape(-1, 2)
+        self.mat_coord_off = np.concatenate([[0], np.cumsum([len(c) for c in mat_xy])]).astype(np.int64)
+        self.mat_coords = cat(mat_xy, np.float64, 2) if mat_xy else np.zeros((0, 2))
+        self.default_E_nu = np.asarray(dflt, dtype=np.float64).reshape(-1, 2)
+        self.n_regions = np.array([len(nm) for nm in self.names], dtype=np.int64)
+        nv = mv[self.sample_mesh]
+        nc = mc[self.sample_mesh]
+        self.vtx_off = np.concatenate([[0], np.cumsum(nv)]).astype(np.int64)
+        self.cell_off = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
+        self.desc = ConditionsDesc(
+            n_meshes=self.n_meshes, n_samples=self.n, nodes_per_cell=k, reserved=0,
+            mesh_vtx_off=ptr(self.mesh_vtx_off), mesh_cell_off=ptr(self.mesh_cell_off), xy=ptr(self.xy), conn=ptr(self.conn),
+            sample_mesh=ptr(self.sample_mesh),
+            vforce_off=ptr(self.vforce_off), vforce_tag=ptr(self.vforce_tag), vforce_mag=ptr(self.vforce_mag),
+            eforce_off=ptr(self.eforce_off), eforce_tag=ptr(self.eforce_tag), eforce_mag=ptr(self.eforce_mag),
+            vfix_off=ptr(self.vfix_off), vfix_tag=ptr(self.vfix_tag), efix_off=ptr(self.efix_off), efix_tag=ptr(self.efix_tag),
+            mat_off=ptr(self.mat_off), mat_E_nu=ptr(self.mat_E_nu), mat_coord_off=ptr(self.mat_coord_off),
+            mat_coords=ptr(self.mat_coords), default_E_nu=ptr(self.default_E_nu))
+
+    @property
+    def n_vertices(self) -> int:
+        return int(self.vtx_off[-1])
+
+    @property
+    def n_cells(self) -> int:
+        return int(self.cell_off[-1])
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(sum(getattr(self, f).nbytes for f in (
+            "mesh_vtx_off", "mesh_cell_off", "xy", "conn", "sample_mesh", "vforce_off", "vforce_tag", "vforce_mag",
+            "eforce_off", "eforce_tag", "eforce_mag", "vfix_off", "vfix_tag", "efix_off", "efix_tag", "mat_off",
+            "mat_E_nu", "mat_coord_off", "mat_coords", "default_E_nu")))
+
+    def split_vertices(self, a: np.ndarray) -> List[np.ndarray]:
+        return [a[self.vtx_off[s]:self.vtx_off[s + 1]] for s in range(self.n)]
+
+    def sample_conn(self, s: int) -> np.ndarray:
+        m = int(self.sample_mesh[s])
+        return self.conn[self.mesh_cell_off[m]:self.mesh_cell_off[m + 1]]
+
+    def sample_coors(self, s: int) -> np.ndarray:
+        m = int(self.sample_mesh[s])
+        return self.xy[self.mesh_vtx_off[m]:self.mesh_vtx_off[m + 1]]
+
+
+@dataclass
+class DeviceSetup:
+    """What the device derived from the conditions (fea_batch_get_setup / _get_materials)."""
+    fixed: np.ndarray          # (n_vertices,) uint8
+    cell_region: np.ndarray    # (n_cells,) int8
+    rhs: np.ndarray            # (n_vertices, 2)
+    region_count: List[np.ndarray]   # per sample: vertices of every region
+    region_flags: List[np.ndarray]   # per sample: (n_regions, n_v) uint8
+    D: List[np.ndarray]        # per sample: (n_used, 3, 3)
 
 
 def pack(samples: Sequence[Sample], alloc=None) -> PackedBatch:
@@ -181,6 +315,11 @@ class Context:
     def create_batch(self, packed: PackedBatch) -> "Batch":
         return Batch(self, packed)
 
+    def create_batch_from_conditions(self, packed: "PackedConditions") -> "Batch":
+        """fea_batch_create_from_conditions: region selection / Dirichlet mask / material cells / load on
+        the device, from tags, magnitudes and coordinate lists."""
+        return Batch(self, packed)
+
     def solve_batch(self, packed: PackedBatch, rtol: float = 1e-10, max_iter: int = 20000,
                     image_size: int = 0, affine: Optional[np.ndarray] = None, value_scale: float = 1.0,
                     out: Optional[BatchResult] = None) -> BatchResult:
@@ -208,7 +347,10 @@ class Batch:
     def __init__(self, ctx: Context, packed: PackedBatch):
         self.ctx, self.packed = ctx, packed
         h = C.c_void_p()
-        ctx._check(ctx.lib.fea_batch_create(ctx.h, C.byref(packed.desc), C.byref(h)))
+        if isinstance(packed, PackedConditions):
+            ctx._check(ctx.lib.fea_batch_create_from_conditions(ctx.h, C.byref(packed.desc), C.byref(h)))
+        else:
+            ctx._check(ctx.lib.fea_batch_create(ctx.h, C.byref(packed.desc), C.byref(h)))
         self.h = h
         self.image_size = 0
 
@@ -267,9 +409,50 @@ class Batch:
             self.ctx._check(self.ctx.lib.fea_batch_rasterize_flags(self.h, ptr(off), ptr(flat), ptr(out)))
         return [out[off[s]:off[s + 1]] for s in range(len(counts))]
 
+    # ---- batches made from conditions -------------------------------------------------------
+    def setup(self, flags: bool = True) -> DeviceSetup:
+        """Download what the device set-up derived (parity tests, text files of the dataset)."""
+        p = self.packed
+        nv, nc = p.n_vertices, p.n_cells
+        fixed, creg, rhs = np.empty(nv, np.uint8), np.empty(nc, np.int8), np.empty((nv, 2))
+        nreg = p.n_regions
+        cnt = np.empty(int(nreg.sum()), np.int32)
+        per_v = np.diff(p.vtx_off)
+        fl = np.empty(int((nreg * per_v).sum()), np.uint8) if flags else None
+        self.ctx._check(self.ctx.lib.fea_batch_get_setup(self.h, ptr(fixed), ptr(creg), ptr(rhs), ptr(cnt), ptr(fl)))
+        reg_off, n_used = np.empty(p.n + 1, np.int32), np.empty(p.n, np.int32)
+        self.ctx._check(self.ctx.lib.fea_batch_get_materials(self.h, ptr(reg_off), ptr(n_used), None))
+        D = np.empty((int(reg_off[-1]), 3, 3))
+        self.ctx._check(self.ctx.lib.fea_batch_get_materials(self.h, None, None, ptr(D)))
+        ro = np.concatenate([[0], np.cumsum(nreg)])
+        fo = np.concatenate([[0], np.cumsum(nreg * per_v)])
+        return DeviceSetup(
+            fixed=fixed, cell_region=creg, rhs=rhs,
+            region_count=[cnt[ro[s]:ro[s + 1]] for s in range(p.n)],
+            region_flags=[fl[fo[s]:fo[s + 1]].reshape(int(nreg[s]), int(per_v[s])) for s in range(p.n)] if flags else [],
+            D=[D[reg_off[s]:reg_off[s] + n_used[s]] for s in range(p.n)])
+
+    def rasterize_regions(self, with_plate_mask: Optional[Sequence[bool]] = None) -> List[np.ndarray]:
+        """Region images of every sample from the device-resident flags; a sample flagged in
+        ``with_plate_mask`` gets the plate mask (input.png) as one more image at the end."""
+        p = self.packed
+        m = np.zeros(p.n, np.uint8) if with_plate_mask is None else np.ascontiguousarray(with_plate_mask, dtype=np.uint8)
+        counts = p.n_regions + m
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        out = np.empty((int(off[-1]), self.image_size, self.image_size), np.uint8)
+        self.ctx._check(self.ctx.lib.fea_batch_rasterize_regions(self.h, ptr(m), ptr(out)))
+        return [out[off[s]:off[s + 1]] for s in range(p.n)]
+
+    def classify(self):
+        """(floating_parts, empty_vertices) per sample: the derived well-posedness check (A-19)."""
+        n = self.packed.n
+        a, z = np.empty(n, np.int32), np.empty(n, np.int32)
+        self.ctx._check(self.ctx.lib.fea_batch_classify(self.h, ptr(a), ptr(z)))
+        return a, z
+
     def cell_strain_stress(self, stress_region: int = -1):
         """(strain, stress), each (n_cells, 3): final-step cell averages (e11, e22, 2e12), D*strain."""
-        nc = len(self.packed.conn)
+        nc = self.packed.n_cells
         strain, stress = np.empty((nc, 3)), np.empty((nc, 3))
         self.ctx._check(self.ctx.lib.fea_batch_cell_strain_stress(self.h, int(stress_region), ptr(strain), ptr(stress)))
         return strain, stress
@@ -298,14 +481,14 @@ class Batch:
         return a, z
 
     def conn(self):
-        c = np.empty_like(self.packed.conn)
+        c = np.empty((self.packed.n_cells, self.packed.k), np.int32)
         f = np.empty(self.packed.n, np.int32)
         self.ctx._check(self.ctx.lib.fea_batch_get_conn(self.h, ptr(c), ptr(f)))
         return c, f
 
     def element_stiffness(self) -> np.ndarray:
         k = self.packed.k
-        ke = np.empty((len(self.packed.conn), 2 * k, 2 * k))
+        ke = np.empty((self.packed.n_cells, 2 * k, 2 * k))
         self.ctx._check(self.ctx.lib.fea_batch_get_element_stiffness(self.h, ptr(ke)))
         return ke
 

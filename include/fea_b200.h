@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define FEA_VERSION_MAJOR 0
-#define FEA_VERSION_MINOR 2
+#define FEA_VERSION_MINOR 3
 
 typedef struct fea_ctx fea_ctx;
 typedef struct fea_batch fea_batch;
@@ -82,6 +82,57 @@ typedef struct fea_batch_desc {
                                    N_regions * sum of point-load magnitudes (F2/F3,
                                    fea_analysis.py:313-359) */
 } fea_batch_desc;
+
+/*
+ * The same n_samples problems described the way the reference's FEAnalysis constructor receives
+ * them (fea_analysis.py:32-48): 1-based point tags, force magnitudes and the per-material
+ * coordinate lists -- NOT derived arrays.  fea_batch_create_from_conditions runs the region
+ * selection of FEAnalysis.__init__ on the device (fea_analysis.py:76-146, 182-194, 235-252):
+ *   'vertex k' regions            tag - 1 (negative indices wrap like numpy's), :196-233
+ *   _get_points_on_edge           |x1*y2 - x2*y1| < 1e-14 w.r.t. the infinite line through the two
+ *                                 tagged vertices, evaluated without FMA contraction, :182-188;
+ *                                 kind 'facet': only vertices of mesh edges with BOTH ends selected
+ *                                 (SURVEY A-7)
+ *   _get_points_in_list           np.isin(coors, list).all(axis=1): x AND y occur anywhere among the
+ *                                 listed scalars (exact fp64 equality; hash set on the bit patterns,
+ *                                 -0.0 == 0.0, NaN matches nothing), :190-194; kind 'cell': complete
+ *                                 cells only (F4), a cell complete in several regions gets the sum of
+ *                                 their D (A-18)
+ *   edge-force magnitude          F / max(#region vertices, 1), :99-105
+ *   load                          n_terms * sum of the per-vertex magnitudes (F2/F3)
+ *   D                             plane strain from (E, nu), :263-265 (F1)
+ * Several samples may share one mesh (the conditions of a plate): meshes are uploaded once.
+ * Sample s has regions in this order: vertex forces, edge forces, vertex constraints, edge
+ * constraints, material regions (n_regions[s] of them).
+ */
+typedef struct fea_conditions_desc {
+  int32_t n_meshes;
+  int32_t n_samples;
+  int32_t nodes_per_cell;       /* 3 or 4, uniform */
+  int32_t reserved;             /* 0 */
+  const int64_t* mesh_vtx_off;  /* [n_meshes+1] */
+  const int64_t* mesh_cell_off; /* [n_meshes+1] */
+  const double*  xy;            /* [mesh_vtx_off[n_meshes]*2] */
+  const int32_t* conn;          /* [mesh_cell_off[n_meshes]*nodes_per_cell] mesh-local vertex ids */
+  const int32_t* sample_mesh;   /* [n_samples] mesh of each sample */
+  const int32_t* vforce_off;    /* [n_samples+1] force_vertex_tags_magnitudes */
+  const int32_t* vforce_tag;    /* [vforce_off[n]] 1-based point tag */
+  const double*  vforce_mag;    /* [vforce_off[n]*2] (fx, fy) */
+  const int32_t* eforce_off;    /* [n_samples+1] force_edges_tags_magnitudes */
+  const int32_t* eforce_tag;    /* [eforce_off[n]*2] the two bounding point tags */
+  const double*  eforce_mag;    /* [eforce_off[n]*2] total (fx, fy) of the edge */
+  const int32_t* vfix_off;      /* [n_samples+1] constraints_vertex_tags */
+  const int32_t* vfix_tag;      /* [vfix_off[n]] */
+  const int32_t* efix_off;      /* [n_samples+1] constraints_edges_tags */
+  const int32_t* efix_tag;      /* [efix_off[n]*2] */
+  const int32_t* mat_off;       /* [n_samples+1] material regions (material_properties_to_vertices
+                                   in dict order); a sample with none is the single-material problem */
+  const double*  mat_E_nu;      /* [mat_off[n]*2] (E, nu) of each material region */
+  const int64_t* mat_coord_off; /* [mat_off[n]+1] offsets, in points, into mat_coords */
+  const double*  mat_coords;    /* [mat_coord_off[last]*2] the (x, y) lists */
+  const double*  default_E_nu;  /* [n_samples*2] youngs_modulus, poisson_ratio of samples without a
+                                   material table (may be NULL if every sample has one) */
+} fea_conditions_desc;
 
 typedef struct fea_batch_info {
   int64_t n_vertices;       /* total vertices */
@@ -169,6 +220,11 @@ int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
  *            (save_output_images, :526-613; custom_plotter.py:121-193; A-16).
  */
 int  fea_batch_create(fea_ctx* ctx, const fea_batch_desc* desc, fea_batch** out);
+/* The inputs of fea_batch_create / fea_batch_create_from_conditions / fea_batch_rasterize are read by
+ * asynchronous copies on the context's stream: the caller must leave them untouched until the next
+ * call that synchronises the context (fea_batch_download*, fea_ctx_synchronize, fea_solve_batch
+ * returns synchronised). */
+int  fea_batch_create_from_conditions(fea_ctx* ctx, const fea_conditions_desc* desc, fea_batch** out);
 int  fea_batch_assemble(fea_batch* b);
 int  fea_batch_solve(fea_batch* b, double rtol, int32_t max_iter);
 /* affine[4*s..] = (ax, bx, ay, by): pixel = a*world + b; value_scale = t_1 (images are of
@@ -202,6 +258,27 @@ int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
  * (launch t is iteration 32*t): at most cap entries are written, *n_out = number available. */
 int  fea_batch_get_timed_launches(fea_batch* b, int32_t cap, float* spmv_ms, float* update_ms,
                                   int32_t* n_out);
+
+/* ---- what the device set-up of fea_batch_create_from_conditions derived (any pointer may be NULL) --
+ * fixed [n_vertices], cell_region [n_cells] (sample-local material-table index, -1 = no stiffness),
+ * rhs [n_vertices*2]: the arrays fea_batch_desc would have carried, sample after sample;
+ * region_count [total regions]: vertices of every region (an edge force is divided by
+ * max(count, 1) in magnitudes.txt, fea_analysis.py:99-115);
+ * region_flags: sample after sample, one uint8 per (region, vertex), regions in the order of
+ * fea_conditions_desc (the vertex sets regions.vtk / regions_<Region>.png show, :377-381, 508-524). */
+int  fea_batch_get_setup(fea_batch* b, uint8_t* fixed, int8_t* cell_region, double* rhs,
+                         int32_t* region_count, uint8_t* region_flags);
+/* material table: reg_off [n_samples+1] (capacity layout), n_used [n_samples] = terms + overlap
+ * combinations in use, D [reg_off[n_samples]*9] */
+int  fea_batch_get_materials(fea_batch* b, int32_t* reg_off, int32_t* n_used, double* D);
+/* Region images of every sample from the DEVICE-resident flags (after fea_batch_rasterize):
+ * sample s contributes its regions in order, then -- if with_plate_mask && with_plate_mask[s] --
+ * one image of the constant field 1 (input.png, :472-506).  images [sum][size][size] uint8. */
+int  fea_batch_rasterize_regions(fea_batch* b, const uint8_t* with_plate_mask, uint8_t* images);
+/* Derived well-posedness check (SURVEY A-19), after fea_batch_assemble: floating_parts[s] = parts
+ * of the stiffness mesh (cells connected through shared edges) with fewer than two fixed vertices,
+ * empty_vertices[s] = active vertices touching no stiffness cell (the reference's SuperLU-NaN case). */
+int  fea_batch_classify(fea_batch* b, int32_t* floating_parts, int32_t* empty_vertices);
 
 /* ---- inspection entry points used by the parity tests -------------------- */
 /* per-sample reduced sizes: n_active_dofs[s], nnz[s] (scalar CSR) */

@@ -39,7 +39,7 @@ def test_version_call(lib):
     import ctypes as C
     a, b = C.c_int(-1), C.c_int(-1)
     assert lib.fea_version(C.byref(a), C.byref(b)) == 0
-    assert (a.value, b.value) == (0, 2)
+    assert (a.value, b.value) == (0, 3)
 
 
 def test_library_is_sm100a_only():
