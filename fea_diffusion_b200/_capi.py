@@ -20,7 +20,7 @@ EXPORTS = [
     "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
     "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create",
     "fea_batch_create_from_conditions", "fea_batch_get_setup", "fea_batch_get_materials", "fea_batch_rasterize_regions",
-    "fea_batch_classify", "fea_batch_assemble",
+    "fea_batch_classify", "fea_batch_rasterize_cell_components", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
     "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
     "fea_batch_get_timed_launches",
@@ -122,6 +122,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_get_materials": (C.c_int, [P, P, P, P]),
         "fea_batch_rasterize_regions": (C.c_int, [P, P, P]),
         "fea_batch_classify": (C.c_int, [P, P, P]),
+        "fea_batch_rasterize_cell_components": (C.c_int, [P, I32, I32, P, F64, P, P]),
         "fea_batch_assemble": (C.c_int, [P]),
         "fea_batch_solve": (C.c_int, [P, F64, I32]),
         "fea_batch_rasterize": (C.c_int, [P, I32, P, F64]),

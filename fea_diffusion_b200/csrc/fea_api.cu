@@ -516,6 +516,38 @@ int fea_batch_cell_strain_stress(fea_batch* hb, int32_t stress_region, double* s
   return FEA_OK;
 }
 
+int fea_batch_rasterize_cell_components(fea_batch* hb, int32_t stress_region, int32_t n_fields, const int32_t* field_ids,
+                                        double value_scale, uint8_t* images, double* ranges) {
+  if (!hb || !field_ids || n_fields < 1 || n_fields > 4 || (!images && !ranges)) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.rasterized) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_rasterize_cell_components before fea_batch_rasterize");
+  for (int f = 0; f < n_fields; ++f)
+    if (field_ids[f] < 0 || field_ids[f] > 3) return api_fail(ctx, FEA_BAD_ARG, "field id must be 0..3");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  const size_t per = (size_t)b.img_size * b.img_size, nc3 = (size_t)std::max<int64_t>(1, b.NC * 3);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_stress = up(sizeof(double) * nc3), o_ids = o_stress + up(sizeof(double) * nc3), o_rng = o_ids + 256,
+               o_img = o_rng + up(sizeof(double) * 2 * n_fields * b.ns), total = o_img + up((size_t)n_fields * b.ns * per);
+  char* d = nullptr;
+  CK(ctx, cudaMallocAsync((void**)&d, total, st));
+  int32_t ids[4] = {0, 0, 0, 0};
+  for (int f = 0; f < n_fields; ++f) ids[f] = field_ids[f];
+  cudaError_t e = cudaMemcpyAsync(d + o_ids, ids, sizeof(ids), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_cell_strain_stress(b, stress_region, (double*)d, (double*)(d + o_stress));
+  if (e == cudaSuccess)
+    e = launch_raster_cell_fields(b, n_fields, (const int32_t*)(d + o_ids), (const double*)d, (const double*)(d + o_stress),
+                                  value_scale, (double*)(d + o_rng), (uint8_t*)(d + o_img));
+  if (e == cudaSuccess && images) e = cudaMemcpyAsync(images, d + o_img, (size_t)n_fields * b.ns * per, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && ranges) e = cudaMemcpyAsync(ranges, d + o_rng, sizeof(double) * 2 * n_fields * b.ns, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // ids (host array) must outlive the copy
+  cudaFreeAsync(d, st);
+  ctx->c.launches += 3;
+  if (e != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "fea_batch_rasterize_cell_components", e);
+  return FEA_OK;
+}
+
 int fea_batch_download_images(fea_batch* hb, uint8_t* images) {
   if (!hb || !images) return FEA_BAD_ARG;
   fea_ctx* ctx = hb->owner;

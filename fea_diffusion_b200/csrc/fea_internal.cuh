@@ -212,6 +212,8 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
 cudaError_t launch_raster(Batch& b, double value_scale);
 cudaError_t launch_raster_flags(Batch& b, int64_t n_img, const int64_t* d_field_off, const int64_t* d_flag_off,
                                 const uint8_t* d_flags, uint8_t* d_images);
+cudaError_t launch_raster_cell_fields(Batch& b, int n_fields, const int32_t* d_ids, const double* d_strain,
+                                      const double* d_stress, double scale, double* d_ranges, uint8_t* d_images);
 // n_fields vertex-scalar images of one mesh; cell_off2 = device {0, n_cell}
 cudaError_t launch_raster_fields(cudaStream_t st, int npc, int64_t n_v, int64_t n_cell, const int32_t* conn,
                                  const double* xy, const double* affine, const int64_t* cell_off2, int size,

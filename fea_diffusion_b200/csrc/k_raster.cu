@@ -233,6 +233,82 @@ cudaError_t launch_raster_flags(Batch& b, int64_t n_img, const int64_t* d_field_
   return cudaGetLastError();
 }
 
+// Per-cell scalar images of every sample of a batch: component x / y of the final-step cauchy stress /
+// strain cell averages at step 1 (outputs_{stress,strain}_{x,y}.png, reference fea_analysis.py:539-558:
+// fields ("cauchy_stress", "c0") ..., each normalised to its own (min, max)).  Field id: 0 stress_x,
+// 1 stress_y, 2 strain_x, 3 strain_y.  One CTA per (field, sample) finds the range first.
+__device__ __forceinline__ const double* cell_component(int id, const double* strain, const double* stress) {
+  return (id < 2 ? stress : strain) + (id & 1);
+}
+__global__ void k_cell_field_ranges(int ns, const int32_t* __restrict__ ids, const int64_t* __restrict__ cell_off,
+                                    const double* __restrict__ strain, const double* __restrict__ stress,
+                                    double* __restrict__ ranges) {
+  __shared__ double sm[2][8];
+  const int f = blockIdx.x / ns, s = blockIdx.x - f * ns;
+  const double* src = cell_component(ids[f], strain, stress);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double mn = inf, mx = -inf;
+  for (int64_t c = cell_off[s] + threadIdx.x; c < cell_off[s + 1]; c += blockDim.x) {
+    const double v = src[3 * c];
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = mn; sm[1][threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mn = fmin(mn, sm[0][i]); mx = fmax(mx, sm[1][i]); }
+    ranges[2 * blockIdx.x] = mn;
+    ranges[2 * blockIdx.x + 1] = mx;
+  }
+}
+template <int NPC>
+__global__ void k_raster_cell_fields(int ns, int size, int n_fields, const int32_t* __restrict__ ids,
+                                     const int64_t* __restrict__ cell_off, const int32_t* __restrict__ owner,
+                                     const double* __restrict__ strain, const double* __restrict__ stress,
+                                     const double* __restrict__ ranges, double scale, uint8_t* __restrict__ images) {
+  constexpr int SUB = (NPC == 3) ? 1 : 2;
+  const int64_t per = (int64_t)size * size;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)n_fields * ns * per) return;
+  const int f = (int)(gid / (ns * per));
+  const int64_t rem = gid - (int64_t)f * ns * per;
+  const int s = (int)(rem / per);
+  const int64_t lp = rem - (int64_t)s * per;
+  const int32_t o = owner[(int64_t)s * per + lp];
+  uint8_t g = 255;
+  if (o != 0x7fffffff) {
+    const int64_t cell = cell_off[s] + o / SUB;
+    const double val = __dmul_rn(scale, cell_component(ids[f], strain, stress)[3 * cell]);
+    const double vmin = __dmul_rn(scale, ranges[2 * (f * ns + s)]), vmax = __dmul_rn(scale, ranges[2 * (f * ns + s) + 1]);
+    const double rng = __dsub_rn(vmax, vmin);
+    double tt = 0.0;
+    if (rng > 0.0) tt = __ddiv_rn(__dsub_rn(val, vmin), rng);
+    tt = fmin(fmax(tt, 0.0), 1.0);
+    g = (uint8_t)(255.0 - fmin(floor(__dmul_rn(256.0, tt)), 255.0));
+  }
+  images[gid] = g;
+}
+
+cudaError_t launch_raster_cell_fields(Batch& b, int n_fields, const int32_t* d_ids, const double* d_strain,
+                                      const double* d_stress, double scale, double* d_ranges, uint8_t* d_images) {
+  cudaStream_t st = b.ctx->stream;
+  const int T = 256;
+  const int64_t n = (int64_t)n_fields * b.ns * b.img_size * b.img_size;
+  if (n == 0) return cudaSuccess;
+  k_cell_field_ranges<<<n_fields * b.ns, 256, 0, st>>>(b.ns, d_ids, b.d_cell_off, d_strain, d_stress, d_ranges);
+  const unsigned g = (unsigned)((n + T - 1) / T);
+  if (b.npc == 3)
+    k_raster_cell_fields<3><<<g, T, 0, st>>>(b.ns, b.img_size, n_fields, d_ids, b.d_cell_off, b.owner, d_strain, d_stress, d_ranges, scale, d_images);
+  else
+    k_raster_cell_fields<4><<<g, T, 0, st>>>(b.ns, b.img_size, n_fields, d_ids, b.d_cell_off, b.owner, d_strain, d_stress, d_ranges, scale, d_images);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_raster(Batch& b, double value_scale) {
   cudaStream_t st = b.ctx->stream;
   const int T = 256;

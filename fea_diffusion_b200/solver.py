@@ -228,6 +228,30 @@ class BatchResult:
     stats: Optional[dict] = None
 
 
+class PinnedArena:
+    """A reusable block of page-locked host memory handed out as numpy arrays: staging buffers of a
+    pipeline step are carved from it (``empty``) and recycled with ``reset`` -- no page faults, no
+    cudaHostAlloc per step.  Falls back to pageable memory when a request does not fit."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.buf = ctx.pinned_empty((int(nbytes),), np.uint8)
+        self.off = 0
+        self.spilled = 0
+
+    def reset(self):
+        self.off = 0
+
+    def empty(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        o = (self.off + 63) // 64 * 64
+        if o + n > self.buf.size:
+            self.spilled += 1
+            return np.empty(shape, dtype)
+        self.off = o + n
+        return self.buf[o:o + n].view(dtype).reshape(shape)
+
+
 class Context:
     """One fea_ctx: a GPU and a stream.  Not thread-safe; use one per host thread."""
 
@@ -385,14 +409,16 @@ class Batch:
         self.image_size = size
         return self
 
-    def download(self, images: bool = False) -> BatchResult:
+    def download(self, images: bool = False, out: Optional[BatchResult] = None) -> BatchResult:
+        """``out`` recycles the host arrays of an earlier result (e.g. pinned ones)."""
         n, nv = self.packed.n, self.packed.n_vertices
-        r = BatchResult(u=np.empty((nv, 2)), ranges=np.empty((n, 4)), iters=np.empty(n, np.int32),
-                        relres=np.empty(n), status=np.empty(n, np.int32))
+        r = out if out is not None else BatchResult(u=np.empty((nv, 2)), ranges=np.empty((n, 4)), iters=np.empty(n, np.int32),
+                                                    relres=np.empty(n), status=np.empty(n, np.int32))
         self.ctx._check(self.ctx.lib.fea_batch_download(self.h, ptr(r.u), ptr(r.ranges), ptr(r.iters),
                                                         ptr(r.relres), ptr(r.status)))
         if images:
-            r.images = np.empty((n, 2, self.image_size, self.image_size), np.uint8)
+            if r.images is None or r.images.shape != (n, 2, self.image_size, self.image_size):
+                r.images = np.empty((n, 2, self.image_size, self.image_size), np.uint8)
             self.ctx._check(self.ctx.lib.fea_batch_download_images(self.h, ptr(r.images)))
         r.stats = self.stats()
         return r
@@ -432,14 +458,18 @@ class Batch:
             region_flags=[fl[fo[s]:fo[s + 1]].reshape(int(nreg[s]), int(per_v[s])) for s in range(p.n)] if flags else [],
             D=[D[reg_off[s]:reg_off[s] + n_used[s]] for s in range(p.n)])
 
-    def rasterize_regions(self, with_plate_mask: Optional[Sequence[bool]] = None) -> List[np.ndarray]:
+    def rasterize_regions(self, with_plate_mask: Optional[Sequence[bool]] = None, out: Optional[np.ndarray] = None) -> List[np.ndarray]:
         """Region images of every sample from the device-resident flags; a sample flagged in
         ``with_plate_mask`` gets the plate mask (input.png) as one more image at the end."""
         p = self.packed
         m = np.zeros(p.n, np.uint8) if with_plate_mask is None else np.ascontiguousarray(with_plate_mask, dtype=np.uint8)
         counts = p.n_regions + m
         off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        out = np.empty((int(off[-1]), self.image_size, self.image_size), np.uint8)
+        shape = (int(off[-1]), self.image_size, self.image_size)
+        if out is None or out.size < int(np.prod(shape)):
+            out = np.empty(shape, np.uint8)
+        else:
+            out = out.reshape(-1)[:int(np.prod(shape))].reshape(shape)
         self.ctx._check(self.ctx.lib.fea_batch_rasterize_regions(self.h, ptr(m), ptr(out)))
         return [out[off[s]:off[s + 1]] for s in range(p.n)]
 
@@ -449,6 +479,19 @@ class Batch:
         a, z = np.empty(n, np.int32), np.empty(n, np.int32)
         self.ctx._check(self.ctx.lib.fea_batch_classify(self.h, ptr(a), ptr(z)))
         return a, z
+
+    CELL_FIELDS = {"stress_x": 0, "stress_y": 1, "strain_x": 2, "strain_y": 3}
+
+    def rasterize_cell_components(self, stress_region: int, names: Sequence[str], value_scale: float = 1.0):
+        """Images + final-step ranges of stress / strain components of every sample
+        (fea_batch_rasterize_cell_components): ({name: (n, size, size) uint8}, {name: (n, 2) f64})."""
+        ids = np.array([self.CELL_FIELDS[nm] for nm in names], np.int32)
+        n = self.packed.n
+        img = np.empty((len(ids), n, self.image_size, self.image_size), np.uint8)
+        rng = np.empty((len(ids), n, 2))
+        self.ctx._check(self.ctx.lib.fea_batch_rasterize_cell_components(self.h, int(stress_region), len(ids), ptr(ids),
+                                                                         float(value_scale), ptr(img), ptr(rng)))
+        return {nm: img[i] for i, nm in enumerate(names)}, {nm: rng[i] for i, nm in enumerate(names)}
 
     def cell_strain_stress(self, stress_region: int = -1):
         """(strain, stress), each (n_cells, 3): final-step cell averages (e11, e22, 2e12), D*strain."""

@@ -25,7 +25,7 @@ class WorkItem:
 
 
 def plate_conditions(seed: int, conditions_per_plate: int, image_size: int, mesh_size: float = 1e-2,
-                     well_posed: bool = True, max_draws: int = 400):
+                     well_posed: bool = True, max_draws: int = 400, extra_as_sampled: int = 0):
     """All conditions of one plate.  With ``well_posed`` the condition sampler is redrawn until
     every stiffness-connected component carries >= 2 fixed vertices and no active vertex is
     isolated (SURVEY A-19); the number of rejected draws is returned for the report."""
@@ -49,18 +49,44 @@ def plate_conditions(seed: int, conditions_per_plate: int, image_size: int, mesh
             rejected += 1
             continue
         items.append(WorkItem(seed, len(items), setup, kw, window, bounds, affine, bounds[2] - bounds[0]))
+    if extra_as_sampled:
+        # further draws of the same plate exactly as the sampler produces them (the reference's own
+        # distribution, a third of it singular by construction): condition dicts only,
+        # the device derives everything else (fea_batch_create_from_conditions)
+        extra = [condition_kwargs(c) for c in gen.sample_conditions(ptags, ltags, extra_as_sampled)]
+        return items, rejected, extra
     return items, rejected
 
 
 def build_workload(n_plates: int, conditions_per_plate: int = 4, image_size: int = 64, seed0: int = 0,
-                   mesh_size: float = 1e-2, well_posed: bool = True):
+                   mesh_size: float = 1e-2, well_posed: bool = True, extra_as_sampled: int = 0):
+    """(items, rejected draws[, as-sampled condition kwargs per plate])."""
     items: List[WorkItem] = []
     rejected = 0
+    extras = []
     for p in range(n_plates):
-        it, rj = plate_conditions(seed0 + p, conditions_per_plate, image_size, mesh_size, well_posed)
-        items.extend(it)
-        rejected += rj
+        r = plate_conditions(seed0 + p, conditions_per_plate, image_size, mesh_size, well_posed,
+                             extra_as_sampled=extra_as_sampled)
+        items.extend(r[0])
+        rejected += r[1]
+        if extra_as_sampled:
+            extras.append(r[2])
+    if extra_as_sampled:
+        return items, rejected, extras
     return items, rejected
+
+
+def conditions_of(items: List[WorkItem]):
+    """(meshes, samples) for ``solver.PackedConditions``: the distinct plate meshes of ``items`` and
+    one (mesh index, FEAnalysis kwargs) pair per item -- the in-memory form of what the reference's
+    generate loop hands to FEAnalysis (generate.py:88-107)."""
+    meshes, samples, index = [], [], {}
+    for it in items:
+        if it.plate not in index:
+            index[it.plate] = len(meshes)
+            meshes.append((it.setup.coors, it.setup.conn))
+        samples.append((index[it.plate], it.kwargs))
+    return meshes, samples
 
 
 def refine_uniform(coors: np.ndarray, conn: np.ndarray, levels: int):
@@ -82,3 +108,35 @@ def refine_uniform(coors: np.ndarray, conn: np.ndarray, levels: int):
                                np.stack([ca, bc, c], 1), np.stack([ab, bc, ca], 1)])
         coors = np.concatenate([coors, mid])
     return np.ascontiguousarray(coors), np.ascontiguousarray(conn.astype(np.int32))
+
+
+def large_case(name: str, levels: int, fixtures_path: str = None):
+    """BASELINE config 3: the reference's cantilever / gusset application problems
+    (applications/cantilever/cantilever.py:43-52, applications/gusset/gusset.py:39-94) on their
+    meshes refined ``levels`` times (the ``refine_mesh`` hook, cantilever.py:26-27).  Returns
+    (ProblemSetup, n_coarse_vertices): the coarse mesh's vertices keep their indices under refinement."""
+    import os
+    if fixtures_path is None:
+        fixtures_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fixtures.npz")
+    F = np.load(fixtures_path)
+    c0, n0 = F[name + "_coors"], F[name + "_conn"]
+    co, cn = refine_uniform(c0, n0, levels)
+    setup = ProblemSetup(co, cn)
+    topo = MeshTopology(setup.conn, len(co))
+    from .host import vertices_on_line
+    if name == "cantilever":
+        fixed = topo.facet_vertices(np.flatnonzero(co[:, 0] < 0.01))
+        loads = [(np.array([3]), (0.0, -1000.0))]
+    elif name == "gusset":
+        fixed = topo.facet_vertices(np.flatnonzero((co[:, 1] < 0.01) | (co[:, 0] < 0.01)))
+        loads = [(topo.facet_vertices(np.flatnonzero(co[:, 0] > 0.99)), (1000.0, 0.0)),
+                 (topo.facet_vertices(vertices_on_line(co, (3, 4))), (1000.0, 1000.0))]
+    else:
+        raise ValueError(name)
+    s = setup.sample
+    s.fixed[:] = False
+    s.fixed[fixed] = True
+    s.rhs[:] = 0
+    for v, m in loads:
+        s.rhs[v] += m
+    return setup, len(c0)

@@ -4,9 +4,11 @@
     python generate_data.py --num_plates 100 --conditions_per_plate 4 --steps_per_condition 11 \\
         --image_size 64 --save_displacement --data_dir data [--gpus 8] [--backend batched|dropin]
 
-`--backend dropin` runs the reference's own sequential loop (datagen.generate.generate_data over
-the CUDA-backed FEAnalysis); `--backend batched` (default) runs the pipelined, sharded generator
-(fea_diffusion_b200.dataset) -- one process per GPU, plates dealt round-robin, no communication.
+`--backend batched` (default) runs the pipelined, sharded generator (fea_diffusion_b200.dataset) --
+one process per GPU, plates dealt round-robin, no communication.  `--backend dropin` runs the
+reference's OWN sequential loop, unchanged, over the CUDA-backed FEAnalysis: it needs a checkout of
+the reference (`--reference_dir` or FEA_REFERENCE_DIR), whose datagen/generate.py is loaded with its
+imports bound to the drop-in classes (fea_diffusion_b200.datagen.generate.load_reference_generate).
 BASELINE.json spells two flags differently from the reference (`--num_conditions_per_plate`,
 `--num_steps`): both spellings are accepted.  `--mesh_size` is a float here (the reference declares
 it `type=int`, which makes every value but the default unusable)."""
@@ -39,6 +41,8 @@ def parse(argv=None):
     ap.add_argument("--wandb_project", type=str, help="Wandb project name.")
     ap.add_argument("--wandb_restrict_cache", type=int, default=10, help="Restrict wandb cache.")
     ap.add_argument("--backend", choices=["batched", "dropin"], default="batched")
+    ap.add_argument("--reference_dir", type=str, default=os.environ.get("FEA_REFERENCE_DIR"),
+                    help="checkout of namanxkumar/fea-diffusion for --backend dropin")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the plates over (batched).")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--plates_per_batch", type=int, default=50)
@@ -53,25 +57,30 @@ def main(argv=None):
     import __graft_entry__ as ge
     ge.build()
     if a.backend == "dropin":
-        from fea_diffusion_b200.datagen import generate_data
-        generate_data(data_dir=a.data_dir, image_size=a.image_size, num_plates=a.num_plates, start_plate=a.start_plate,
-                      conditions_per_plate=a.conditions_per_plate, mesh_size=a.mesh_size,
-                      save_displacement=a.save_displacement, save_strain=a.save_strain, save_stress=a.save_stress,
-                      num_steps_per_condition=a.steps_per_condition, save_meshes=a.save_meshes, random_seed=a.seed)
+        if not a.reference_dir:
+            sys.exit("--backend dropin runs the reference's own datagen/generate.py: pass --reference_dir")
+        from fea_diffusion_b200.datagen.generate import load_reference_generate
+        load_reference_generate(a.reference_dir)(
+            data_dir=a.data_dir, image_size=a.image_size, num_plates=a.num_plates, start_plate=a.start_plate,
+            conditions_per_plate=a.conditions_per_plate, mesh_size=a.mesh_size, save_displacement=a.save_displacement,
+            save_strain=a.save_strain, save_stress=a.save_stress, num_steps_per_condition=a.steps_per_condition,
+            save_meshes=a.save_meshes)
         return
-    if a.save_strain or a.save_stress:
-        print("note: the batched backend writes strain/stress into the .vtk files (--save_meshes); "
-              "their images are produced by --backend dropin", file=sys.stderr)
     start = max(0, (a.start_plate - 1) if a.start_plate is not None else 0)   # reference generate.py:50 quirk
     if a.gpus > 1 and a.rank is None:
         procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--rank", str(r)])
                  for r in range(a.gpus)]
-        sys.exit(max(p.wait() for p in procs))
+        codes = [p.wait() for p in procs]          # negative = killed by a signal (e.g. -9: out of memory)
+        for r, rc in enumerate(codes):
+            if rc != 0:
+                print("rank %d failed with exit code %d: its plates are missing from %s" % (r, rc, a.data_dir), file=sys.stderr)
+        sys.exit(1 if any(rc != 0 for rc in codes) else 0)
     from fea_diffusion_b200.dataset import generate_dataset
     rank = a.rank or 0
     st = generate_dataset(a.data_dir, a.num_plates, a.conditions_per_plate, a.image_size, a.steps_per_condition,
                           a.mesh_size, seed=a.seed, rank=rank, world=a.gpus, plates_per_batch=a.plates_per_batch,
-                          save_meshes=a.save_meshes, start_plate=start,
+                          save_meshes=a.save_meshes, start_plate=start, save_displacement=a.save_displacement,
+                          save_stress=a.save_stress, save_strain=a.save_strain,
                           progress=lambda d, n: print("rank %d: %d / %d plates" % (rank, d, n), flush=True))
     print(json.dumps(st))
 

@@ -252,6 +252,15 @@ int  fea_batch_rasterize_flags(fea_batch* b, const int64_t* field_off, const uin
  * the sample used for EVERY cell (the hook evaluates the single material named 'm' over Omega);
  * -1: each cell's own D, zero for cells without stiffness.  Either pointer may be NULL. */
 int  fea_batch_cell_strain_stress(fea_batch* b, int32_t stress_region, double* strain, double* stress);
+/* Images of stress / strain components of every sample (outputs_{stress,strain}_{x,y}.png,
+ * fea_analysis.py:539-558: cell scalars ("cauchy_stress"|"cauchy_strain", "c0"|"c1"), each normalised
+ * to its own range), after fea_batch_rasterize, same camera and colour map.  field_ids[n_fields]:
+ * 0 stress_x, 1 stress_y, 2 strain_x, 3 strain_y; stress_region as in fea_batch_cell_strain_stress;
+ * images [n_fields][n_samples][size][size] are of value_scale * field (step 1); ranges
+ * [n_fields][n_samples][2] = (min, max) of the FINAL step (ranges.txt lines are t_k multiples). */
+int  fea_batch_rasterize_cell_components(fea_batch* b, int32_t stress_region, int32_t n_fields,
+                                         const int32_t* field_ids, double value_scale, uint8_t* images,
+                                         double* ranges);
 int  fea_batch_get_info(fea_batch* b, fea_batch_info* out);
 int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
 /* CUDA-event durations of the SpMV / update launch that opens each chunk of 32 PCG iterations

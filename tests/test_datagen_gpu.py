@@ -116,13 +116,14 @@ def test_feanalysis_text_files_match_the_committed_composite_condition(tmp_path,
 
 
 def test_generate_data_tree(tmp_path):
-    """generate_data (reference datagen/generate.py) end to end: directory tree and file
-    contents the training set reader expects (model/diffusion.py:134-141, 174-217, 359-378)."""
+    """generate_data (the reference's keyword surface, datagen/generate.py:12-31) end to end: directory
+    tree and file contents the training set reader expects (model/diffusion.py:134-141, 174-217,
+    359-378), incl. the stress / strain images and their ranges.txt lines (fea_analysis.py:539-558)."""
     d = str(tmp_path / "data")
     generate_data(data_dir=d, image_size=64, num_plates=2, conditions_per_plate=2, mesh_size=4e-2,
-                  num_steps_per_condition=5, save_meshes=True, random_seed=11, verbose=False)
-    assert sorted(os.listdir(d)) == ["1", "2", "part.mesh"]
-    co, cn = read_mesh(os.path.join(d, "part.mesh"))   # mesh of the last plate
+                  num_steps_per_condition=5, save_meshes=True, save_stress=True, save_strain=True, seed=11, workers=2)
+    assert sorted(os.listdir(d)) == ["1", "2"]
+    kinds = ["displacement_x", "displacement_y", "stress_x", "stress_y", "strain_x", "strain_y"]
     for plate in ("1", "2"):
         pd = os.path.join(d, plate)
         assert {"1", "2", "input.png", "outline.png"} <= set(os.listdir(pd))
@@ -131,19 +132,26 @@ def test_generate_data_tree(tmp_path):
         for cond in ("1", "2"):
             cd = os.path.join(pd, cond)
             files = set(os.listdir(cd))
-            assert {"outputs_displacement_x.png", "outputs_displacement_y.png", "magnitudes.txt", "materials.txt",
-                    "ranges.txt", "regions.vtk"} <= files
+            assert {"outputs_%s.png" % k for k in kinds} | {"magnitudes.txt", "materials.txt", "ranges.txt", "regions.vtk"} <= files
+            assert "status.txt" not in files                      # only converged solutions are written
             assert {"domain.%d.vtk" % k for k in range(5)} <= files
             assert any(f.startswith("regions_MaterialRegion") for f in files)
-            assert Image.open(os.path.join(cd, "outputs_displacement_x.png")).size == size
+            for k in kinds:
+                assert Image.open(os.path.join(cd, "outputs_%s.png" % k)).size == size
             lines = open(os.path.join(cd, "ranges.txt")).read().splitlines()
-            assert [l.split(":")[0] for l in lines] == ["displacement_%s_%d" % (c, k) for k in range(1, 5) for c in "xy"]
-            _, _, p4, _ = read_vtk(os.path.join(cd, "domain.4.vtk"))
+            assert [l.split(":")[0] for l in lines] == ["%s_%d" % (k, st) for st in range(1, 5) for k in kinds]
+            _, _, p4, c4 = read_vtk(os.path.join(cd, "domain.4.vtk"))
             _, _, p1, _ = read_vtk(os.path.join(cd, "domain.1.vtk"))
             assert np.allclose(p1["u"], 0.25 * p4["u"], rtol=1e-14, atol=0)
-            lo, hi = eval(lines[-2].split(":", 1)[1])
+            final = dict(l.split(":", 1) for l in lines[-6:])
+            lo, hi = eval(final["displacement_x_4"])
             assert lo == p4["u"][:, 0].min() and hi == p4["u"][:, 0].max()
-    assert len(co) == len(p4["u"])
+            lo, hi = eval(final["stress_y_4"])
+            assert lo == c4["cauchy_stress"][:, 1].min() and hi == c4["cauchy_stress"][:, 1].max()
+            lo, hi = eval(final["strain_x_4"])
+            assert lo == c4["cauchy_strain"][:, 0].min() and hi == c4["cauchy_strain"][:, 0].max()
+            img = np.array(Image.open(os.path.join(cd, "outputs_stress_x.png")))[:, :, 0]
+            assert img.min() < 128 and (img == 255).any()         # own range: dark at the extreme cells, white background
 
 
 def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
@@ -153,7 +161,7 @@ def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
     from fea_diffusion_b200.dataset import generate_dataset
     from fea_diffusion_b200.workload import plate_conditions
     kw = dict(conditions_per_plate=2, image_size=64, num_steps=5, mesh_size=5e-2, seed=7, plates_per_batch=2,
-              workers=2, save_meshes=True)
+              workers=2, save_meshes=True, save_stress=True, save_strain=True)
     d1 = str(tmp_path / "one")
     st = generate_dataset(d1, 3, **kw)
     assert st["plates"] == 3 and st["samples"] == 6
@@ -178,7 +186,7 @@ def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
         assert an.calculate()
         an.update_image_size_or_bounds(image_size=it.window, bounds=it.bounds)
         an.save_region_images(os.path.join(cond_dir, "regions"))
-        an.save_output_images(os.path.join(cond_dir, "outputs"), save_stress=False, save_strain=False)
+        an.save_output_images(os.path.join(cond_dir, "outputs"), save_stress=True, save_strain=True)
         got = os.path.join(d1, "2", str(ci + 1))
         for f in sorted(os.listdir(cond_dir)):
             if f.endswith(".png"):
