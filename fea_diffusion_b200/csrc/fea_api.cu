@@ -383,6 +383,8 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.x, b.NBR * 2));
   CK(ctx, dalloc(b, &b.rp, b.NBR * 4));
   CK(ctx, dalloc(b, &b.q, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.xlo, b.NBR * 2));
+  CK(ctx, dalloc(b, &b.sb, b.NBR * 2));
   const int64_t ncta = b.NBR / kCtaRows;
   CK(ctx, dalloc(b, &b.active_cta, 4 * ncta));  // int4 entries
   CK(ctx, dalloc(b, &b.partA, ncta));

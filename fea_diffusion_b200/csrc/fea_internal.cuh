@@ -123,6 +123,7 @@ struct Batch {
   // solver vectors: x, q [NBR*2]; rp [NBR*4] = one 32-byte record (r.x, r.y, p.x, p.y) per block
   // row, so that a neighbour's residual and search direction arrive with ONE 256-bit gather
   double *x = nullptr, *rp = nullptr, *q = nullptr;
+  double *xlo = nullptr, *sb = nullptr;       // [NBR*2] low part of refined solutions; S b (extended-precision rounds)
   double *partA = nullptr, *partB = nullptr;  // [NBR/kCtaRows]
   SysScalars sc{};
   double* rz_last = nullptr;   // [ns] r.z at exit

@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(kT) k_pcg_init_vectors(const PcgPtrs* __restri
   P.x[row] = z;
   P.rp[row] = rec;
   P.q[row] = z;
+  const_cast<double2*>(P.sb)[row] = b;   // kept for the extended-precision rounds of the on-chip path
   const double part = cta_sum(fma(b.x, b.x, b.y * b.y), sm);
   if (threadIdx.x == 0) P.partB[blockIdx.x] = part;
 }
@@ -428,6 +429,9 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   }
   P.cl_counter = b.cl_counter;
   P.cl_halo_cap = b.ctx->cluster_halo_cap;
+  P.refine_dd = b.ctx->refine_rounds > 0 ? 1 : 0;
+  P.xlo = (double2*)b.xlo;
+  P.sb = (const double2*)b.sb;
   return P;
 }
 

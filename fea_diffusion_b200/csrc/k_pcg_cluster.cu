@@ -21,8 +21,10 @@
 //   * NO cluster barrier inside the iteration: the three hand-overs (halo of p, p.q partials, r.r
 //     partials) complete on mbarrier transaction counts in the receiving CTA; a warp waits for the
 //     halo only when it reaches a slice that reads it;
-//   * a converged system is verified against its TRUE residual (and restarted once if the gap is
-//     material); every 1024 iterations the same pass monitors progress and stops mechanisms.
+//   * a converged system is verified against its TRUE residual; if fp64 CG cannot reach the
+//     tolerance (the floor eps |K| |x| of an ill-conditioned plate) it is finished by iterative
+//     refinement with a double-double residual; every 1024 iterations the same pass monitors
+//     progress and stops mechanisms.
 //
 // Clusters are persistent and pull systems from a queue (longest job first), so there is no
 // lock-step and no tail of idle CTAs waiting for the slowest system of a batch.  HBM traffic is one
@@ -86,8 +88,10 @@ constexpr int kClTmpBytes = 2 * kClWords * 4 + 128;   // halo bitmap + its prefi
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
   double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
   double partB[kClMax * kClW];    // r.r partials (each warp pushes its partial to all CTAs)
-  double rz_monitor;              // true r.r at the previous monitor pass
-  double tol2;                    // rtol^2 * r0.r0 of the current system
+  double rz_monitor;              // smallest true r.r any monitor pass has seen
+  double tol2;                    // rtol^2 * r0.r0 of the current system (tightened by an extended-precision round)
+  int32_t mon_strikes;            // consecutive monitor passes without a 4x gain on rz_monitor
+  int32_t pad2_;
   uint64_t mbarA, mbarB, mbarP;   // transaction barriers: p.q partials / r.r partials / halo of p have landed
   int32_t it_limit;               // iteration budget of the current system (tightened after a restart)
   int32_t next_sys;               // (rank 0) queue entry the cluster works on next
@@ -186,6 +190,97 @@ __device__ __forceinline__ double sum_table(const double* t, int lane) {
     if (lane + 32 * i < CL * kClW) acc += t[lane + 32 * i];
   return warp_sum(acc);
 }
+
+// ---- extended-precision refinement ------------------------------------------------------------
+// fp64 CG cannot push the TRUE residual b - K x below ~eps * |K| * max_k |x_k| (the recursion
+// r -= alpha q and the product K x both round at that level).  On plates with a weakly held part
+// (kappa ~ 1e7 and beyond; the residual climbs by orders of magnitude before it falls) that floor is
+// above the tolerance: the recursive residual converges, the true one stalls around 1e-7, and the
+// displacement is off by more than the 1e-8 the reference's direct solve is matched to.  Such a
+// system is finished by iterative refinement: x is kept as an unevaluated sum xhi + xlo, the true
+// residual is formed in double-double arithmetic (error-free products and sums, ~1e-30), and the
+// SAME fp64 CG solves K d = r for the correction, which only has to gain a few digits per round.
+// The rounds run on the rows' owners through global memory (a few per 1000 systems; the vectors are
+// L2 resident), out of line so that the registers of the iteration are untouched.
+struct dd2 { double hi, lo; };
+__device__ __forceinline__ dd2 two_sum(double a, double b) {
+  const double s = __dadd_rn(a, b);
+  const double bb = __dsub_rn(s, a);
+  return dd2{s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
+}
+__device__ __forceinline__ dd2 quick_two_sum(double a, double b) {   // |a| >= |b|
+  const double s = __dadd_rn(a, b);
+  return dd2{s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+__device__ __forceinline__ dd2 dd_add(dd2 a, double bh, double bl) {
+  const dd2 s = two_sum(a.hi, bh);
+  return quick_two_sum(s.hi, __dadd_rn(__dadd_rn(s.lo, a.lo), bl));
+}
+// acc -= k * (xh + xl), the product k * xh taken exactly (fma residual)
+__device__ __forceinline__ dd2 dd_msub(dd2 acc, double k, double xh, double xl) {
+  const double p = __dmul_rn(k, xh);
+  const double e = __fma_rn(k, xl, __fma_rn(k, xh, -p));
+  return dd_add(acc, -p, -e);
+}
+// x (hi, lo) += d for this thread's rows; first = the sum starts from d alone
+__device__ __forceinline__ void dd_fold_rows(const PcgPtrs& P, int64_t my_row0, int n_own, int tid, const double2 (&d)[kClRpt], bool first) {
+#pragma unroll
+  for (int k = 0; k < kClRpt; ++k) {
+    const int lr = tid + kClT * k;
+    if (lr >= n_own) continue;
+    double2 hi = d[k], lo = make_double2(0.0, 0.0);
+    if (!first) {
+      const double2 h0 = P.x[my_row0 + lr], l0 = P.xlo[my_row0 + lr];
+      const dd2 a = dd_add(dd2{h0.x, l0.x}, d[k].x, 0.0), b = dd_add(dd2{h0.y, l0.y}, d[k].y, 0.0);
+      hi = make_double2(a.hi, b.hi);
+      lo = make_double2(a.lo, b.lo);
+    }
+    P.x[my_row0 + lr] = hi;
+    P.xlo[my_row0 + lr] = lo;
+  }
+}
+// r = S b - Khat (xhi + xlo) for this thread's rows, in double-double, rounded once; written into
+// the (r.x, r.y) fields of the row records (the right-hand side of the correction solve);
+// returns the thread's part of r.r
+__device__ __noinline__ double dd_residual_rows(const PcgPtrs* Pp, int64_t my_row0, int n_own, int tid) {
+  const PcgPtrs& P = *Pp;
+  double part = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < kClRpt; ++k) {
+    const int lr = tid + kClT * k;
+    if (lr >= n_own) continue;
+    const int64_t row = my_row0 + lr;
+    const int lane = (int)(row & 31);
+    const int L = P.slice_len[row >> 5];
+    const int64_t base = P.slice_ptr[row >> 5] + lane;
+    const double2 b = P.sb[row], xh = __ldcg(P.x + row), xl = __ldcg(P.xlo + row);
+    const double a = P.dcoup[row];
+    dd2 r0{b.x, 0.0}, r1{b.y, 0.0};
+    r0 = dd_add(r0, -xh.x, -xl.x);            // diagonal block [[1, a], [a, 1]]
+    r0 = dd_msub(r0, a, xh.y, xl.y);
+    r1 = dd_msub(r1, a, xh.x, xl.x);
+    r1 = dd_add(r1, -xh.y, -xl.y);
+#pragma unroll 1
+    for (int j = 0; j < L; ++j) {
+      const int c = P.col[base + (int64_t)j * 32];
+      const d4 kv = P.val[base + (int64_t)j * 32];
+      const double2 ch = __ldcg(P.x + c), cl = __ldcg(P.xlo + c);
+      r0 = dd_msub(r0, kv.x, ch.x, cl.x);
+      r0 = dd_msub(r0, kv.y, ch.y, cl.y);
+      r1 = dd_msub(r1, kv.z, ch.x, cl.x);
+      r1 = dd_msub(r1, kv.w, ch.y, cl.y);
+    }
+    d4 rec = P.rp[row];
+    rec.x = __dadd_rn(r0.hi, r0.lo);
+    rec.y = __dadd_rn(r1.hi, r1.lo);
+    P.rp[row] = rec;
+    part = fma(rec.x, rec.x, fma(rec.y, rec.y, part));
+  }
+  return part;
+}
+constexpr int kMaxRefine = 3;            // extended-precision rounds per system
+constexpr double kRefineTighten = 1e-4;  // a refined system is solved to rtol / 100: what stalls fp64 CG also
+                                         // amplifies the residual into the displacement (measured: 200x)
 
 template <int CL>
 __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const PcgPtrs* __restrict__ Pp) {
@@ -436,16 +531,20 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     if (tid == 0) {                           // loop constants that are needed once per iteration live in
       h->tol2 = P.sc.tol2[s];                 // shared memory: registers are the scarce resource here
       h->it_limit = P.max_iter;
-      h->rz_monitor = inf;                    // true r.r found by the last monitor pass
+      h->rz_monitor = inf;                    // smallest true r.r found by a monitor pass
+      h->mon_strikes = 0;
     }
     __syncthreads();
     int iters = 0, status = FEA_SAMPLE_NOT_RUN;
 #ifdef FEA_CLUSTER_ACCOUNT
     const long long acc_t2 = clock64();
 #endif
-    bool restarted = false;
     bool monitored = false;                   // the monitor pass of the current iteration count is done
+    bool gap = false;                         // the recursive residual converged, the TRUE one did not (fp64 floor)
+    int refine_round = 0;                     // extended-precision rounds done; > 0: the solution is (P.x, P.xlo)
+    double rz_round = inf;                    // true r.r at the start of the current refinement round
 
+    for (;;) {   // ---- refinement rounds: one pass for all but the ill-conditioned systems ----------------
     for (;;) {
       // A converged system gets one more pass through the SpMV machinery in "check" mode: the
       // published vector is x, and r is REPLACED by the true residual S b - Khat x (the recursion
@@ -620,9 +719,16 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k)
           if (own[k]) pbuf[tid + kClT * k] = P.q[my_row0 + tid + kClT * k];
-        const bool stuck = !(rz_new < 0.25 * h->rz_monitor);    // |r| not even halved in the interval
+        // no progress = the true |r| has not even halved against the best value any pass has seen, for two
+        // passes in a row (a slowly converging but well-posed system -- kappa ~ 1e7 -- gains about that much
+        // per interval, and CG residuals are not monotone)
+        const bool gained = rz_new < 0.25 * h->rz_monitor;
+        const bool stuck = !gained && h->mon_strikes >= 1;
         __syncthreads();
-        if (tid == 0) h->rz_monitor = rz_new;
+        if (tid == 0) {
+          h->mon_strikes = gained ? 0 : h->mon_strikes + 1;
+          h->rz_monitor = fmin(h->rz_monitor, rz_new);
+        }
         rz = rz_new;
         if (stuck || !isfinite(rz_new)) {
           status = FEA_SAMPLE_STAGNATED;
@@ -633,23 +739,15 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       if (check) {
         rz = rz_new;                                            // what relres reports: the TRUE residual
         const double tol2 = *(volatile double*)&h->tol2;
-        const int max_iter = *(volatile int32_t*)&h->it_limit;
         if (!(rz_new > 100.0 * tol2 && isfinite(rz_new))) {     // true residual within 10x the tolerance
           if (isfinite(rz_new)) status = FEA_SAMPLE_CONVERGED;
           break;
         }
-        if (restarted || iters >= max_iter || status != FEA_SAMPLE_CONVERGED) {
-          status = FEA_SAMPLE_STAGNATED;
-          break;
-        }
-        restarted = true;                                       // restart from x with the true residual
-        if (rank == 0 && tid == 0) atomicAdd(P.cl_counter, 1);
-        status = FEA_SAMPLE_NOT_RUN;
-        rz_prev = inf;                                          // beta = 0
-        const int c2 = iters + iters / 4 + 100;
-        __syncthreads();                                        // everybody has read the old limit
-        if (tid == 0) h->it_limit = c2 < max_iter ? c2 : max_iter;
-        continue;
+        // the recursion says converged, b - K x says no: the fp64 floor of this system is above the
+        // tolerance.  Left to an extended-precision round (below) -- or reported, if those are off.
+        gap = status == FEA_SAMPLE_CONVERGED;
+        status = FEA_SAMPLE_STAGNATED;
+        break;
       }
       rz_prev = rz;
       rz = rz_new;
@@ -657,10 +755,59 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       monitored = false;
     }
 
-    // ---- results ------------------------------------------------------------------------------
+      // ---- extended-precision round (see dd_residual_rows) --------------------------------------
+      // entered when fp64 CG hit its floor (gap), and after every correction solve to fold the
+      // correction in and verify the sum against its double-double residual
+      if (!(P.refine_dd && ((gap && refine_round == 0) || refine_round > 0) &&
+            (status == FEA_SAMPLE_CONVERGED || status == FEA_SAMPLE_STAGNATED)))
+        break;
+      dd_fold_rows(P, my_row0, my_sl * 32, tid, x, refine_round == 0);
+      __threadfence();
+      cluster.sync();                                            // every CTA's part of xhi + xlo is visible
+      {
+        double part = warp_sum(dd_residual_rows(Pp, my_row0, my_sl * 32, tid));
+        push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), (uint32_t)offsetof(ClHeader, mbarB), rank, warp, lane, part);
+        await_tx(&h->mbarB, 8u * CL * kClW, (phase >> 1) & 1u, tid);
+        phase ^= 2u;
+        rz = sum_table<CL>(h->partB, lane);                      // TRUE r.r of xhi + xlo, to ~1e-30
+      }
+      const double tol2_ref = kRefineTighten * P.sc.tol2[s];
+      if (rz <= tol2_ref) { status = FEA_SAMPLE_CONVERGED; break; }
+      if (refine_round >= kMaxRefine || !(rz < 0.25 * rz_round) || !isfinite(rz)) { status = FEA_SAMPLE_STAGNATED; break; }
+      // correction solve: Khat d = r, from d = 0, to the (absolute) refined tolerance
+      rz_round = rz;
+      ++refine_round;
+      if (rank == 0 && tid == 0) atomicAdd(P.cl_counter, 1);
 #pragma unroll
-    for (int k = 0; k < kClRpt; ++k)
-      if (own[k]) P.x[my_row0 + tid + kClT * k] = x[k];
+      for (int k = 0; k < kClRpt; ++k) {
+        x[k] = make_double2(0.0, 0.0);
+        r[k] = x[k];
+        if (own[k]) {
+          const d4 rec = P.rp[my_row0 + tid + kClT * k];
+          r[k] = make_double2(rec.x, rec.y);
+          pbuf[tid + kClT * k] = x[k];
+        }
+      }
+      rz_prev = inf;                                             // beta = 0
+      status = FEA_SAMPLE_NOT_RUN;
+      gap = false;
+      monitored = false;
+      __syncthreads();                                           // everybody has read the old constants
+      if (tid == 0) {
+        h->tol2 = tol2_ref;
+        h->it_limit = P.max_iter;
+        h->rz_monitor = inf;
+        h->mon_strikes = 0;
+      }
+      __syncthreads();
+    }
+
+    // ---- results ------------------------------------------------------------------------------
+    if (refine_round == 0 && !(P.refine_dd && gap)) {            // otherwise P.x already holds the high part of the sum
+#pragma unroll
+      for (int k = 0; k < kClRpt; ++k)
+        if (own[k]) P.x[my_row0 + tid + kClT * k] = x[k];
+    }
 #ifdef FEA_CLUSTER_PROFILE
     if (prof) {
       for (int i = 0; i < 8; ++i) atomicAdd(&g_cl_prof[i], (unsigned long long)h->prof[i]);

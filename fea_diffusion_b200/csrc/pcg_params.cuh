@@ -39,6 +39,10 @@ struct PcgPtrs {
   int32_t* cl_counter;      // [1..8] work-queue heads, [0] restarts, [10] systems handed back to the
                             // streaming kernels (device counters, zeroed per solve)
   int32_t cl_halo_cap;      // largest halo (rows gathered from other CTAs) a CTA accepts (test knob)
+  // extended-precision refinement of the on-chip path (k_pcg_cluster.cu, dd_residual_rows)
+  int32_t refine_dd;        // 1 = systems that hit the fp64 floor get double-double refinement rounds
+  double2* xlo;             // low part of the solution of a refined system (high part: x)
+  const double2* sb;        // S b of every block row, as k_pcg_init_vectors rounded it
 };
 static_assert(sizeof(PcgPtrs) <= kPcgParamBytes, "grow kPcgParamBytes");
 

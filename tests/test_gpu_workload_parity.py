@@ -6,6 +6,7 @@ import pytest
 
 from fea_diffusion_b200 import Context, pack
 from fea_diffusion_b200._capi import SAMPLE_CONVERGED, SAMPLE_STAGNATED
+from fea_diffusion_b200.workload import plate_conditions
 from fea_diffusion_b200.workload import build_workload
 from oracle import raster_oracle as ro
 from oracle.fea_oracle import OracleProblem
@@ -31,10 +32,9 @@ def test_every_sample_of_a_workload_batch_matches_the_oracle():
     for i, it in enumerate(items):
         orc = OracleProblem(it.setup.coors, it.setup.conn, num_steps=11, **it.kwargs)
         assert orc.classify()["well_posed"] == 1
-        assert res.status[i] in (SAMPLE_CONVERGED, SAMPLE_STAGNATED)
-        if res.status[i] != SAMPLE_CONVERGED:          # flagged as too ill-conditioned: not a parity sample
-            assert res.relres[i] > 1e-9
-            continue
+        # the reference's direct solve never fails on a well-posed system (fea_analysis.py:371-375):
+        # every sample must converge -- ill-conditioned ones through the extended-precision rounds
+        assert res.status[i] == SAMPLE_CONVERGED, (i, int(res.status[i]), float(res.relres[i]))
         u = orc.solve("best")
         if not np.any(u[-1]):                           # every loaded vertex is constrained: u == 0 exactly
             assert not np.any(us[i]) and res.iters[i] == 0
@@ -52,5 +52,42 @@ def test_every_sample_of_a_workload_batch_matches_the_oracle():
             worst_px = max(worst_px, d)
             assert d <= 1, (i, c, d)                    # images within 1 LSB
         n_checked += 1
-    assert n_checked >= 44
+    assert n_checked + sum(1 for i in range(48) if res.iters[i] == 0) == 48
     print("workload parity: %d samples, max rel-L2 %.2e, max pixel diff %d" % (n_checked, worst_u, worst_px))
+
+
+def test_ill_conditioned_plate_is_finished_in_extended_precision():
+    """Plate 6 / condition 0 of the bench workload: a weakly held part (the residual climbs 85x before
+    it falls, kappa ~ 1e7).  fp64 CG stalls at a TRUE relative residual of 1.1e-7 although its
+    recursive residual reaches 1e-10, and the displacement is then 4e-8 off sfepy's kind of direct
+    solve.  The on-chip solver detects the gap and finishes with double-double residual rounds;
+    without them (refine_rounds = 0) the sample is reported STAGNATED, never "converged"."""
+    items, _ = plate_conditions(6, 1, 64)
+    it = items[0]
+    orc = OracleProblem(it.setup.coors, it.setup.conn, num_steps=2, **it.kwargs)
+    assert orc.classify()["well_posed"] == 1
+    u = orc.solve("best")[-1]
+    ctx = Context(0)
+    try:
+        packed = pack([it.setup.sample])
+        with ctx.create_batch(packed) as b:
+            r = b.assemble().solve(1e-10, 50000).download()
+            st = b.stats()
+        assert r.status[0] == SAMPLE_CONVERGED and st["refined_systems"] >= 1 and st["cluster_systems"] == 1
+        assert r.relres[0] <= 1e-11                                 # solved to rtol / 100, TRUE residual
+        err = float(np.linalg.norm(r.u - u) / np.linalg.norm(u))
+        assert err <= 1e-8, err
+        ctx.set_option("refine_rounds", 0)
+        with ctx.create_batch(packed) as b:
+            r0 = b.assemble().solve(1e-10, 50000).download()
+        assert r0.status[0] == SAMPLE_STAGNATED and r0.relres[0] > 1e-9
+        # the same bits whatever else shares the batch (two copies + another plate)
+        ctx.set_option("refine_rounds", 1)
+        other, _ = plate_conditions(3, 1, 64)
+        with ctx.create_batch(pack([other[0].setup.sample, it.setup.sample, it.setup.sample])) as b:
+            r3 = b.assemble().solve(1e-10, 50000).download()
+        n = len(it.setup.coors)
+        assert np.array_equal(r3.u[-n:], r.u) and np.array_equal(r3.u[-2 * n:-n], r.u) and r3.iters[2] == r.iters[0]
+    finally:
+        ctx.close()
+    print("ill-conditioned plate: %d iterations, relres %.2e, rel-L2 vs direct solve %.2e" % (r.iters[0], r.relres[0], err))
