@@ -22,7 +22,7 @@ EXPORTS = [
     "fea_batch_create_from_conditions", "fea_batch_get_setup", "fea_batch_get_materials", "fea_batch_rasterize_regions",
     "fea_batch_classify", "fea_batch_rasterize_cell_components", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
-    "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats",
+    "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats", "fea_batch_get_refine_rounds",
     "fea_batch_get_timed_launches",
     "fea_batch_sample_sizes", "fea_batch_get_conn", "fea_batch_get_element_stiffness",
     "fea_batch_get_csr", "fea_batch_spmv", "fea_rasterize_fields", "fea_solve_batch",
@@ -131,6 +131,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_download_images": (C.c_int, [P, P]),
         "fea_batch_get_info": (C.c_int, [P, C.POINTER(BatchInfo)]),
         "fea_batch_get_solve_stats": (C.c_int, [P, C.POINTER(SolveStats)]),
+        "fea_batch_get_refine_rounds": (C.c_int, [P, P]),
         "fea_batch_get_timed_launches": (C.c_int, [P, I32, P, P, P]),
         "fea_batch_sample_sizes": (C.c_int, [P, P, P]),
         "fea_batch_get_conn": (C.c_int, [P, P, P]),

@@ -398,6 +398,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.sc.iters, b.ns));
   CK(ctx, dalloc(b, &b.sc.cap, b.ns));
   CK(ctx, dalloc(b, &b.sc.rz_mon, b.ns));
+  CK(ctx, dalloc(b, &b.sc.rounds, b.ns));
   CK(ctx, dalloc(b, &b.sc.status, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumA, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumB, b.ns));
@@ -606,6 +607,17 @@ int fea_batch_get_info(fea_batch* hb, fea_batch_info* out) {
   out->block_rows = rows;
   out->sell_blocks = b.n_blocks;
   out->max_row_blocks = b.max_row_blocks;
+  return FEA_OK;
+}
+
+int fea_batch_get_refine_rounds(fea_batch* hb, int32_t* rounds) {
+  if (!hb || !rounds) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.solved) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_get_refine_rounds before fea_batch_solve");
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaMemcpyAsync(rounds, b.sc.rounds, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, ctx->c.stream));
+  CK(ctx, cudaStreamSynchronize(ctx->c.stream));
   return FEA_OK;
 }
 

@@ -57,6 +57,7 @@ struct SysScalars {
   int32_t* iters;
   int32_t* cap;      // iteration budget of the current (re)start; < max_iter only after a reopen
   double* rz_mon;    // true r.r at the previous monitor pass (streaming path)
+  int32_t* rounds;   // extended-precision refinement rounds the system needed (0 for all but ill-conditioned ones)
   int32_t* status;
   double* psumA;     // per-system sums of the CTA partials (two-level mode, huge systems only)
   double* psumB;

@@ -391,6 +391,7 @@ __global__ void k_pcg_init_scalars(const PcgPtrs* __restrict__ Pp, const int32_t
   P.sc.iters[s] = 0;
   P.sc.cap[s] = P.max_iter;
   P.sc.rz_mon[s] = __longlong_as_double(0x7ff0000000000000LL);
+  P.sc.rounds[s] = 0;
   int st = FEA_SAMPLE_NOT_RUN, dn = 0;
   if (empty[s]) { st = FEA_SAMPLE_EMPTY_ROW; dn = 1; }
   else if (!(total > 0.0)) { st = isfinite(total) ? FEA_SAMPLE_CONVERGED : FEA_SAMPLE_BREAKDOWN; dn = 1; }

@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       P.sc.iters[s] = iters;
       P.sc.status[s] = status;
       P.sc.cap[s] = -1;     // verified against the true residual on chip: skip the streaming check
+      P.sc.rounds[s] = refine_round;
       P.sc.done[s] = 1;
       P.rz_last[s] = rz;
       atomicAdd(P.sc.n_done, 1);

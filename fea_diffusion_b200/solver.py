@@ -510,6 +510,12 @@ class Batch:
         self.ctx._check(self.ctx.lib.fea_batch_get_solve_stats(self.h, C.byref(s)))
         return s.as_dict()
 
+    def refine_rounds(self) -> np.ndarray:
+        """Extended-precision rounds per sample (> 0: an ill-conditioned system, see fea_b200.h)."""
+        r = np.empty(self.packed.n, np.int32)
+        self.ctx._check(self.ctx.lib.fea_batch_get_refine_rounds(self.h, ptr(r)))
+        return r
+
     def timed_launches(self):
         """(spmv_ms, update_ms) arrays: launch t opened iteration 32*t of the last solve."""
         a, u = np.zeros(64, np.float32), np.zeros(64, np.float32)

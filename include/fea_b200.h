@@ -53,9 +53,11 @@ enum fea_sample_status {
   FEA_SAMPLE_BREAKDOWN = 2,  /* p^T A p <= 0 or non-finite: matrix not SPD (floating region, F4) */
   FEA_SAMPLE_EMPTY_ROW = 3,  /* an active vertex touches no stiffness cell: exactly singular
                                 (the reference's SuperLU-NaN -> calculate() False path, A-18) */
-  FEA_SAMPLE_STAGNATED = 4   /* the recursive residual met rtol but the true residual b - K x stays
-                                above 10 rtol even after a restart: too ill-conditioned for fp64 CG at
-                                this tolerance; u is the best iterate, relres its TRUE residual */
+  FEA_SAMPLE_STAGNATED = 4   /* no progress: the TRUE residual b - K x stopped falling (a mechanism the
+                                classifier missed, an inconsistent system), or it stays above 10 rtol
+                                although the recursive residual met rtol and the extended-precision
+                                rounds could not close the gap (or are switched off, "refine_rounds" 0);
+                                u is the best iterate, relres its TRUE residual */
 };
 
 /*
@@ -160,8 +162,8 @@ typedef struct fea_solve_stats {
   int64_t cluster_iterations;  /* sum of their iteration counts */
   float   cluster_ms;          /* CUDA-event duration of the group of per-size kernels */
   int32_t cluster_size;        /* CTAs per cluster (1..8) of the class that solved most systems */
-  /* residual replacement: systems whose TRUE residual b - K x missed the tolerance after the
-   * recursive one had met it, and that were therefore restarted from their current x */
+  /* systems whose TRUE residual b - K x missed the tolerance after the recursive one had met it:
+   * extended-precision refinement rounds (on-chip path) / restarts from the true residual (streaming) */
   int32_t refined_systems;
   int32_t pad_;
 } fea_solve_stats;
@@ -194,8 +196,10 @@ int  fea_ctx_wait_ctx(fea_ctx* ctx, fea_ctx* other);
  *                   code, 2 = strips, 3 = auto (default: keep a numbering that is already local,
  *                   sort by strips otherwise).  It decides how local the SpMV gathers are, never
  *                   what is exported (fea_batch_get_csr always follows sfepy's numbering)
- *   "refine_rounds" restarts from the true residual per solve (default 1; 0 = the true residual
- *                   is only checked and reported)
+ *   "refine_rounds" 0 = the true residual of a converged system is only checked and reported;
+ *                   > 0 (default 1) = a system that misses the tolerance on its true residual is
+ *                   finished by extended-precision refinement (on-chip path, up to 3 rounds) or
+ *                   restarted from the true residual that many times (streaming path)
  *   "cluster_halo_cap"  test knob: the largest number of rows a CTA of the on-chip path accepts
  *                   from its cluster peers (default: whatever fits its shared memory); a system
  *                   above it is handed back to the streaming kernels
@@ -263,6 +267,13 @@ int  fea_batch_rasterize_cell_components(fea_batch* b, int32_t stress_region, in
                                          double* ranges);
 int  fea_batch_get_info(fea_batch* b, fea_batch_info* out);
 int  fea_batch_get_solve_stats(fea_batch* b, fea_solve_stats* out);
+/* rounds [n_samples]: extended-precision refinement rounds each sample needed.  0 for ordinary
+ * systems.  > 0 marks a system whose fp64 CG stalled above the tolerance (kappa ~ 1e7 and beyond: a
+ * weakly held part): it was finished by iterative refinement with a double-double residual and solved
+ * to rtol / 100, relres is that residual.  For such a system ANY fp64 solve -- the reference's SuperLU
+ * included -- is only defined to about kappa * eps: one rounding of the matrix entries moves the
+ * direct solve's own answer by ~1e-8 (tests/test_gpu_workload_parity.py measures it). */
+int  fea_batch_get_refine_rounds(fea_batch* b, int32_t* rounds);
 /* CUDA-event durations of the SpMV / update launch that opens each chunk of 32 PCG iterations
  * (launch t is iteration 32*t): at most cap entries are written, *n_out = number available. */
 int  fea_batch_get_timed_launches(fea_batch* b, int32_t cap, float* spmv_ms, float* update_ms,
