@@ -86,13 +86,16 @@ constexpr int kClWpt = kClWords / kClT;     // bitmap words per thread (consecut
 constexpr int kClTmpBytes = 2 * kClWords * 4 + 128;   // halo bitmap + its prefix sums (set-up only)
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
-  double partA[kClMax * kClW];    // p.q partials of every warp of every CTA of the cluster
-  double partB[kClMax * kClW];    // r.r partials (each warp pushes its partial to all CTAs)
+  // one hand-over per iteration: every warp pushes the record (p.q, q.q, r.q, r.r) of its rows to all CTAs;
+  // two tables + two barriers used alternately, so that a warp that runs ahead can never write into the
+  // table a slower warp is still summing, nor complete bytes on a phase that has not opened yet
+  alignas(32) double partA[2][kClMax * kClW * 4];
+  double partB[kClMax * kClW];    // r.r partials of the true-residual passes (check / monitor / refinement)
   double rz_monitor;              // smallest true r.r any monitor pass has seen
   double tol2;                    // rtol^2 * r0.r0 of the current system (tightened by an extended-precision round)
   int32_t mon_strikes;            // consecutive monitor passes without a 4x gain on rz_monitor
   int32_t pad2_;
-  uint64_t mbarA, mbarB, mbarP;   // transaction barriers: p.q partials / r.r partials / halo of p have landed
+  uint64_t mbarA[2], mbarB, mbarP; // transaction barriers: iteration records (even / odd) / true-residual partials / halo of p
   int32_t it_limit;               // iteration budget of the current system (tightened after a restart)
   int32_t next_sys;               // (rank 0) queue entry the cluster works on next
   int32_t n_send;                 // entries of this CTA's send list
@@ -181,6 +184,36 @@ __device__ __forceinline__ void push_partial(ClHeader* h, uint32_t field_off, ui
                  "d"(v), "r"(base + mbar_off)
                  : "memory");
   }
+}
+// The iteration's record: lane c < CL of every warp sends (p.q, q.q, r.q, r.r) of the warp's rows to slot
+// [rank][warp] of CTA c's table (two 16-byte st.async).  The sum: lane l adds component l & 3 of the records
+// l >> 2, (l >> 2) + 8, ... (consecutive doubles across the lanes: conflict-free), three butterfly steps
+// combine the lanes of a component, four broadcasts hand every lane all four totals -- the same order
+// in every warp of every CTA, hence the same bits.
+template <int CL>
+__device__ __forceinline__ void push_record(ClHeader* h, int buf, int rank, int warp, int lane, double a, double b, double c, double d) {
+  if (lane < CL) {
+    const uint32_t base = mapa_u32(smem_u32(h), lane);   // the header of CTA `lane`
+    const uint32_t dst = base + (uint32_t)offsetof(ClHeader, partA) + (uint32_t)buf * (uint32_t)sizeof(h->partA[0]) +
+                         32u * (uint32_t)(rank * kClW + warp);
+    const uint32_t bar = base + (uint32_t)offsetof(ClHeader, mbarA) + 8u * (uint32_t)buf;
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst), "d"(a), "d"(b), "r"(bar) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst + 16u), "d"(c), "d"(d), "r"(bar) : "memory");
+  }
+}
+template <int CL>
+__device__ __forceinline__ void sum_records(const double* t, int lane, double& a, double& b, double& c, double& d) {
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < (CL * kClW * 4 + 31) / 32; ++i)
+    if (lane + 32 * i < CL * kClW * 4) acc += t[lane + 32 * i];
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  a = __shfl_sync(0xffffffffu, acc, 0);
+  b = __shfl_sync(0xffffffffu, acc, 1);
+  c = __shfl_sync(0xffffffffu, acc, 2);
+  d = __shfl_sync(0xffffffffu, acc, 3);
 }
 template <int CL>
 __device__ __forceinline__ double sum_table(const double* t, int lane) {
@@ -295,12 +328,13 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const uint32_t smem_a = smem_u32(smem);
-  uint32_t phase = 0;   // bits 0 / 1 / 2: parity of the next p.q / r.r / halo phase
+  uint32_t phase = 0;   // bits 0 / 3: parity of the next phase of the even / odd record barrier; bit 1: true-residual partials; bit 2: halo
 #ifdef FEA_CLUSTER_ACCOUNT
   const long long acc_t0 = clock64();   // SM-cycle accounting: CTA lifetime / system set-up / iterations
 #endif
   if (tid == 0) {
-    mbar_init(smem_u32(&h->mbarA), 1);
+    mbar_init(smem_u32(&h->mbarA[0]), 1);
+    mbar_init(smem_u32(&h->mbarA[1]), 1);
     mbar_init(smem_u32(&h->mbarB), 1);
     mbar_init(smem_u32(&h->mbarP), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -514,9 +548,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       x[k] = make_double2(0.0, 0.0);
       r[k] = x[k];
       if (own[k]) {
-        pbuf[lr] = x[k];
         const d4 rec = P.rp[my_row0 + lr];   // r0 = S b (k_pcg_init_vectors)
         r[k] = make_double2(rec.x, rec.y);
+        pbuf[lr] = r[k];                     // first direction p = r
         dcs[lr] = P.dcoup[my_row0 + lr];
       }
     }
@@ -527,7 +561,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       h->prof[9] = clock64();
     }
 #endif
-    double rz = P.sc.rz[0][s], rz_prev = inf;
+    double rz = P.sc.rz[0][s];
     if (tid == 0) {                           // loop constants that are needed once per iteration live in
       h->tol2 = P.sc.tol2[s];                 // shared memory: registers are the scarce resource here
       h->it_limit = P.max_iter;
@@ -545,45 +579,30 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     double rz_round = inf;                    // true r.r at the start of the current refinement round
 
     for (;;) {   // ---- refinement rounds: one pass for all but the ill-conditioned systems ----------------
+    // CG with ONE hand-over per iteration.  After q = Khat p every warp pushes the record
+    //   (p.q, q.q, r.q, r.r)  of its rows; with the four sums every thread knows
+    //   alpha      = r.r / p.q
+    //   |r_new|^2  = r.r - 2 alpha r.q + alpha^2 q.q      (r_new = r - alpha q, expanded)
+    //   beta       = |r_new|^2 / r.r
+    // before touching a vector, so x, r AND the next direction p = r_new + beta p are updated in one
+    // pass.  r.r in the record is the exact norm of the current residual (nothing is accumulated from
+    // iteration to iteration; the expansion only serves beta, where a relative error of
+    // eps r.r / |r_new|^2 tilts the next direction by that much), and it is what convergence is
+    // decided on -- one SpMV later than in the textbook loop (+1 SpMV per solve).
+    //
+    // mode 0 = iteration; mode 1 / 2 = "check" / "monitor": the published vector is x and r is REPLACED
+    // by the true residual S b - Khat x (the recursion r -= alpha q drifts by rounding).  A converged
+    // system is checked once; a material gap goes to the extended-precision rounds below.  The monitor
+    // pass runs every kMonitor iterations (2 kMonitor for the 5..8-CTA classes, whose convergence curves
+    // have longer plateaus): p is parked in the global q rows meanwhile, so CG continues undisturbed; a
+    // system whose TRUE residual does not fall any more is not going to converge (singular or
+    // inconsistent: a mechanism the classifier missed, F4) and is stopped as STAGNATED instead of
+    // holding its cluster for max_iter iterations.
+    int mode = 0;
     for (;;) {
-      // A converged system gets one more pass through the SpMV machinery in "check" mode: the
-      // published vector is x, and r is REPLACED by the true residual S b - Khat x (the recursion
-      // r -= alpha q drifts by rounding).  A material gap restarts CG once from the current x.
-      //
-      // The same pass runs every kMonitor iterations (2 kMonitor for the larger systems of the
-      // 5..8-CTA classes, whose convergence curves have longer plateaus) while the system is iterating
-      // ("monitor"): r is replaced by the true residual, p is parked in the global q rows and put
-      // back afterwards, so CG continues undisturbed.  A system whose TRUE residual has not even
-      // halved since the previous monitor pass is not going to converge (singular or inconsistent:
-      // a mechanism the classifier missed, F4) and is stopped as STAGNATED instead of holding its
-      // cluster for max_iter iterations.
-      bool check = false, monitor = false;
-      if (status == FEA_SAMPLE_NOT_RUN) {
-        if (!isfinite(rz)) status = FEA_SAMPLE_BREAKDOWN;
-        else if (rz <= *(volatile double*)&h->tol2) status = FEA_SAMPLE_CONVERGED;
-        else if (iters >= *(volatile int32_t*)&h->it_limit)
-          status = *(volatile int32_t*)&h->it_limit < P.max_iter ? FEA_SAMPLE_STAGNATED : FEA_SAMPLE_MAX_ITER;
-        if (status != FEA_SAMPLE_NOT_RUN) {
-          if ((status == FEA_SAMPLE_CONVERGED || status == FEA_SAMPLE_STAGNATED) && iters > 0) check = true;
-          else break;
-        } else if (!monitored && iters > 0 && (iters & ((CL > 4 ? 2 * kMonitor : kMonitor) - 1)) == 0) {
-          check = monitor = monitored = true;
-        }
-      }
-      const double beta = rz / rz_prev;
-#pragma unroll
-      for (int k = 0; k < kClRpt; ++k) {
-        if (own[k]) {
-          double2 pv = pbuf[tid + kClT * k];
-          if (monitor) P.q[my_row0 + tid + kClT * k] = pv;
-          pv.x = check ? x[k].x : fma(beta, pv.x, r[k].x);
-          pv.y = check ? x[k].y : fma(beta, pv.y, r[k].y);
-          pbuf[tid + kClT * k] = pv;
-        }
-      }
       PROF_T(0);
-      // S1: the CTA's new p is complete (bar.sync) and its boundary rows are pushed into the halo
-      // slots of the CTAs that gather them.  A warp waits for this CTA's own halo only when it reaches
+      // S1: the CTA's published vector is complete (bar.sync) and its boundary rows are pushed into the
+      // halo slots of the CTAs that gather them.  A warp waits for this CTA's own halo only when it reaches
       // a slice that gathers from it (the few slices along the CTA's borders) or at the end of its
       // SpMV: the flight time of the pushes is hidden behind the interior slices.
       __syncthreads();
@@ -600,14 +619,12 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       bool halo_here = false;
       PROF_T(1);
       double2 q[kClRpt];
-      double part = 0.0;
 #pragma unroll
       for (int k = 0; k < kClRpt; ++k) {
         const int ls = warp + kClW * k;
         double a0 = 0.0, a1 = 0.0;
-        double2 pk = make_double2(0.0, 0.0);
         if (ls < my_sl) {
-          pk = pbuf[tid + kClT * k];
+          const double2 pk = pbuf[tid + kClT * k];
           const double dck = dcs[tid + kClT * k];
           a0 = fma(dck, pk.y, pk.x);
           a1 = fma(dck, pk.x, pk.y);
@@ -668,52 +685,94 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           }
         }
         q[k] = make_double2(a0, a1);
-        part += own[k] ? fma(pk.x, a0, pk.y * a1) : 0.0;
       }
       if (!halo_here) mbar_wait(smem_u32(&h->mbarP), (phase >> 2) & 1u);   // every thread consumes every phase
       phase ^= 4u;
-      if (!check) {
-        part = warp_sum(part);
-        push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partA), (uint32_t)offsetof(ClHeader, mbarA), rank, warp, lane, part);
-        PROF_T(2);
-        await_tx(&h->mbarA, 8u * CL * kClW, phase & 1u, tid);       // S2: p.q partials have landed
-        phase ^= 1u;
-        PROF_T(3);
-        const double pq = sum_table<CL>(h->partA, lane);
-        PROF_T(4);
-        if (!(pq > 0.0 && isfinite(pq))) { status = FEA_SAMPLE_BREAKDOWN; break; }
-        const double alpha = rz / pq;
-        part = 0.0;
-#pragma unroll
-        for (int k = 0; k < kClRpt; ++k) {
-          const double2 pk = own[k] ? pbuf[tid + kClT * k] : make_double2(0.0, 0.0);
-          x[k].x = fma(alpha, pk.x, x[k].x);
-          x[k].y = fma(alpha, pk.y, x[k].y);
-          r[k].x = fma(-alpha, q[k].x, r[k].x);
-          r[k].y = fma(-alpha, q[k].y, r[k].y);
-          part += own[k] ? fma(r[k].x, r[k].x, r[k].y * r[k].y) : 0.0;
-        }
-      } else {
-        part = 0.0;
+      if (mode == 0) {
+        double s_pq = 0.0, s_qq = 0.0, s_rq = 0.0, s_rr = 0.0;
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k) {
           if (own[k]) {
-            const d4 rec = P.rp[my_row0 + tid + kClT * k];      // S b, untouched by this kernel
-            r[k].x = rec.x - q[k].x;
-            r[k].y = rec.y - q[k].y;
-            part += fma(r[k].x, r[k].x, r[k].y * r[k].y);
+            const double2 pk = pbuf[tid + kClT * k];
+            s_pq = fma(pk.x, q[k].x, fma(pk.y, q[k].y, s_pq));
+            s_qq = fma(q[k].x, q[k].x, fma(q[k].y, q[k].y, s_qq));
+            s_rq = fma(r[k].x, q[k].x, fma(r[k].y, q[k].y, s_rq));
+            s_rr = fma(r[k].x, r[k].x, fma(r[k].y, r[k].y, s_rr));
           }
+        }
+        s_pq = warp_sum(s_pq); s_qq = warp_sum(s_qq); s_rq = warp_sum(s_rq); s_rr = warp_sum(s_rr);
+        const int ab = iters & 1;
+        push_record<CL>(h, ab, rank, warp, lane, s_pq, s_qq, s_rq, s_rr);
+        PROF_T(2);
+        await_tx(&h->mbarA[ab], 32u * CL * kClW, (phase >> (ab ? 3 : 0)) & 1u, tid);   // S2: the records have landed
+        phase ^= ab ? 8u : 1u;
+        PROF_T(3);
+        double pq, qq, rq;
+        sum_records<CL>(h->partA[ab], lane, pq, qq, rq, rz);     // rz = r.r of the current residual, exact
+        PROF_T(4);
+        bool check = false, monitor = false;
+        if (!isfinite(rz)) { status = FEA_SAMPLE_BREAKDOWN; break; }
+        if (rz <= *(volatile double*)&h->tol2) {
+          status = FEA_SAMPLE_CONVERGED;
+          if (iters == 0) break;
+          check = true;
+        } else if (iters >= *(volatile int32_t*)&h->it_limit) {
+          status = FEA_SAMPLE_MAX_ITER;
+          break;
+        } else if (!monitored && iters > 0 && (iters & ((CL > 4 ? 2 * kMonitor : kMonitor) - 1)) == 0) {
+          check = monitor = monitored = true;
+        }
+        if (check) {   // publish x instead of p (q of this round is dropped: one SpMV per pass)
+#pragma unroll
+          for (int k = 0; k < kClRpt; ++k) {
+            if (own[k]) {
+              if (monitor) P.q[my_row0 + tid + kClT * k] = pbuf[tid + kClT * k];
+              pbuf[tid + kClT * k] = x[k];
+            }
+          }
+          mode = monitor ? 2 : 1;
+          continue;
+        }
+        if (!(pq > 0.0 && isfinite(pq))) { status = FEA_SAMPLE_BREAKDOWN; break; }
+        const double alpha = rz / pq;
+        const double est = fma(alpha * alpha, qq, fma(-2.0 * alpha, rq, rz));   // |r - alpha q|^2
+        const double beta = est > 0.0 ? est / rz : 0.0;
+#pragma unroll
+        for (int k = 0; k < kClRpt; ++k) {
+          if (own[k]) {
+            double2 pk = pbuf[tid + kClT * k];
+            x[k].x = fma(alpha, pk.x, x[k].x);
+            x[k].y = fma(alpha, pk.y, x[k].y);
+            r[k].x = fma(-alpha, q[k].x, r[k].x);
+            r[k].y = fma(-alpha, q[k].y, r[k].y);
+            pk.x = fma(beta, pk.x, r[k].x);
+            pk.y = fma(beta, pk.y, r[k].y);
+            pbuf[tid + kClT * k] = pk;
+          }
+        }
+        ++iters;
+        monitored = false;
+        PROF_T(5);
+        continue;
+      }
+      // ---- check / monitor: q = Khat x, r := S b - q ------------------------------------------------
+      double part = 0.0;
+#pragma unroll
+      for (int k = 0; k < kClRpt; ++k) {
+        if (own[k]) {
+          const d4 rec = P.rp[my_row0 + tid + kClT * k];      // S b (the correction's right-hand side in a refinement round)
+          r[k].x = rec.x - q[k].x;
+          r[k].y = rec.y - q[k].y;
+          part += fma(r[k].x, r[k].x, r[k].y * r[k].y);
         }
       }
       part = warp_sum(part);
       push_partial<CL>(h, (uint32_t)offsetof(ClHeader, partB), (uint32_t)offsetof(ClHeader, mbarB), rank, warp, lane, part);
-      PROF_T(5);
       await_tx(&h->mbarB, 8u * CL * kClW, (phase >> 1) & 1u, tid);  // S3: r.r partials have landed
       phase ^= 2u;
-      PROF_T(6);
       const double rz_new = sum_table<CL>(h->partB, lane);
-      PROF_T(7);
-      if (monitor) {
+      rz = rz_new;                                              // what relres reports: the TRUE residual
+      if (mode == 2) {
         // every gather of x is done (S3; the halo copies are refreshed by the next push): put p back
         // and continue CG with the true residual as r
 #pragma unroll
@@ -729,15 +788,14 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           h->mon_strikes = gained ? 0 : h->mon_strikes + 1;
           h->rz_monitor = fmin(h->rz_monitor, rz_new);
         }
-        rz = rz_new;
         if (stuck || !isfinite(rz_new)) {
           status = FEA_SAMPLE_STAGNATED;
           break;
         }
+        mode = 0;
         continue;
       }
-      if (check) {
-        rz = rz_new;                                            // what relres reports: the TRUE residual
+      {
         const double tol2 = *(volatile double*)&h->tol2;
         if (!(rz_new > 100.0 * tol2 && isfinite(rz_new))) {     // true residual within 10x the tolerance
           if (isfinite(rz_new)) status = FEA_SAMPLE_CONVERGED;
@@ -745,14 +803,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
         // the recursion says converged, b - K x says no: the fp64 floor of this system is above the
         // tolerance.  Left to an extended-precision round (below) -- or reported, if those are off.
-        gap = status == FEA_SAMPLE_CONVERGED;
+        gap = true;
         status = FEA_SAMPLE_STAGNATED;
         break;
       }
-      rz_prev = rz;
-      rz = rz_new;
-      ++iters;
-      monitored = false;
     }
 
       // ---- extended-precision round (see dd_residual_rows) --------------------------------------
@@ -785,10 +839,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         if (own[k]) {
           const d4 rec = P.rp[my_row0 + tid + kClT * k];
           r[k] = make_double2(rec.x, rec.y);
-          pbuf[tid + kClT * k] = x[k];
+          pbuf[tid + kClT * k] = r[k];                           // first direction p = r
         }
       }
-      rz_prev = inf;                                             // beta = 0
       status = FEA_SAMPLE_NOT_RUN;
       gap = false;
       monitored = false;
@@ -896,7 +949,7 @@ void pcg_cluster_profile_dump() {
                   "iterations x CTAs %llu  (cycles per iteration %.0f)\n",
           h[12], h[10] * 1e-6, h[11] * 1e-6, h[13] * 1e-6, h[14], h[14] ? (double)h[11] / (double)h[14] : 0.0);
 #endif
-  const char* names[8] = {"p publish", "S1 barrier", "spmv + warp partial", "S2 barrier", "sum A", "update", "S3 barrier", "sum B"};
+  const char* names[8] = {"(loop back)", "bar.sync + halo push", "spmv + record push", "wait for records", "sum records", "update x r p", "-", "-"};
   const double it = (double)(h[8] ? h[8] : 1);
   for (int i = 0; i < 8; ++i) fprintf(stderr, "[cluster prof] %-20s %8.0f cycles/iter\n", names[i], h[i] / it);
   unsigned long long z[16] = {};
