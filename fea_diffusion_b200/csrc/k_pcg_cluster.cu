@@ -45,6 +45,11 @@ namespace fea {
 #if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 __device__ unsigned long long g_cl_prof[16];
 #endif
+#ifdef FEA_CLUSTER_DEBUG
+#define DBG(...) do { if (rank == 0 && tid == 0) printf(__VA_ARGS__); } while (0)
+#else
+#define DBG(...) do { } while (0)
+#endif
 #ifdef FEA_CLUSTER_PROFILE
 #define PROF_T(i) do { if (prof) { const long long t_ = clock64(); h->prof[i] += t_ - h->prof[9]; h->prof[9] = t_; } } while (0)
 #else
@@ -590,14 +595,14 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     // eps r.r / |r_new|^2 tilts the next direction by that much), and it is what convergence is
     // decided on -- one SpMV later than in the textbook loop (+1 SpMV per solve).
     //
-    // mode 0 = iteration; mode 1 / 2 = "check" / "monitor": the published vector is x and r is REPLACED
-    // by the true residual S b - Khat x (the recursion r -= alpha q drifts by rounding).  A converged
-    // system is checked once; a material gap goes to the extended-precision rounds below.  The monitor
-    // pass runs every kMonitor iterations (2 kMonitor for the 5..8-CTA classes, whose convergence curves
-    // have longer plateaus): p is parked in the global q rows meanwhile, so CG continues undisturbed; a
-    // system whose TRUE residual does not fall any more is not going to converge (singular or
-    // inconsistent: a mechanism the classifier missed, F4) and is stopped as STAGNATED instead of
-    // holding its cluster for max_iter iterations.
+    // mode 0 = iteration; mode 1 / 2 = "check" / "monitor": the published vector is x and the TRUE
+    // residual S b - Khat x is measured (the recursion r -= alpha q drifts from it by rounding).  A
+    // converged system is checked once; a material gap goes to the extended-precision rounds below.
+    // The monitor pass runs every kMonitor iterations (2 kMonitor for the 5..8-CTA classes, whose
+    // convergence curves have longer plateaus): p is parked in the global q rows meanwhile and CG
+    // continues undisturbed; a system whose TRUE residual does not fall any more is not going to
+    // converge (singular or inconsistent: a mechanism the classifier missed, F4) and is stopped as
+    // STAGNATED instead of holding its cluster for max_iter iterations.
     int mode = 0;
     for (;;) {
       PROF_T(0);
@@ -711,6 +716,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         sum_records<CL>(h->partA[ab], lane, pq, qq, rq, rz);     // rz = r.r of the current residual, exact
         PROF_T(4);
         bool check = false, monitor = false;
+#ifdef FEA_CLUSTER_DEBUG
+        if ((iters & 127) == 0 || (iters > 1020 && iters < 1030)) DBG("[cl] sys %d it %d rr/rr0 %.3e pq %.3e qq %.3e rq %.3e\n", s, iters, rz / P.sc.rz0[s], pq, qq, rq);
+#endif
         if (!isfinite(rz)) { status = FEA_SAMPLE_BREAKDOWN; break; }
         if (rz <= *(volatile double*)&h->tol2) {
           status = FEA_SAMPLE_CONVERGED;
@@ -755,15 +763,17 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         PROF_T(5);
         continue;
       }
-      // ---- check / monitor: q = Khat x, r := S b - q ------------------------------------------------
+      // ---- check / monitor: q = Khat x; the TRUE residual S b - q is only measured, never put into the
+      // recursion: once CG runs below the fp64 floor of the true residual (eps |K| |x|, see the
+      // extended-precision rounds) a replaced r is orders of magnitude larger than the direction it is
+      // combined with, and the iteration blows up (observed on the ill-conditioned bench plate)
       double part = 0.0;
 #pragma unroll
       for (int k = 0; k < kClRpt; ++k) {
         if (own[k]) {
           const d4 rec = P.rp[my_row0 + tid + kClT * k];      // S b (the correction's right-hand side in a refinement round)
-          r[k].x = rec.x - q[k].x;
-          r[k].y = rec.y - q[k].y;
-          part += fma(r[k].x, r[k].x, r[k].y * r[k].y);
+          const double t0 = rec.x - q[k].x, t1 = rec.y - q[k].y;
+          part += fma(t0, t0, t1 * t1);
         }
       }
       part = warp_sum(part);
@@ -771,10 +781,11 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       await_tx(&h->mbarB, 8u * CL * kClW, (phase >> 1) & 1u, tid);  // S3: r.r partials have landed
       phase ^= 2u;
       const double rz_new = sum_table<CL>(h->partB, lane);
-      rz = rz_new;                                              // what relres reports: the TRUE residual
+      if (mode == 1) rz = rz_new;                               // what relres reports: the TRUE residual
+      DBG("[cl] sys %d it %d mode %d true rr/rr0 %.3e (tol2/rr0 %.3e)\n", s, iters, mode, rz_new / P.sc.rz0[s], h->tol2 / P.sc.rz0[s]);
       if (mode == 2) {
         // every gather of x is done (S3; the halo copies are refreshed by the next push): put p back
-        // and continue CG with the true residual as r
+        // and continue CG undisturbed
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k)
           if (own[k]) pbuf[tid + kClT * k] = P.q[my_row0 + tid + kClT * k];
@@ -790,6 +801,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         }
         if (stuck || !isfinite(rz_new)) {
           status = FEA_SAMPLE_STAGNATED;
+          rz = rz_new;
           break;
         }
         mode = 0;
@@ -812,8 +824,8 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       // ---- extended-precision round (see dd_residual_rows) --------------------------------------
       // entered when fp64 CG hit its floor (gap), and after every correction solve to fold the
       // correction in and verify the sum against its double-double residual
-      if (!(P.refine_dd && ((gap && refine_round == 0) || refine_round > 0) &&
-            (status == FEA_SAMPLE_CONVERGED || status == FEA_SAMPLE_STAGNATED)))
+      // (a correction whose solve was stopped by the monitor or ran out of iterations is dropped)
+      if (!(P.refine_dd && ((gap && refine_round == 0) || (refine_round > 0 && (gap || status == FEA_SAMPLE_CONVERGED)))))
         break;
       dd_fold_rows(P, my_row0, my_sl * 32, tid, x, refine_round == 0);
       __threadfence();
@@ -826,6 +838,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         rz = sum_table<CL>(h->partB, lane);                      // TRUE r.r of xhi + xlo, to ~1e-30
       }
       const double tol2_ref = kRefineTighten * P.sc.tol2[s];
+      DBG("[cl] sys %d it %d round %d status %d dd rr/rr0 %.3e\n", s, iters, refine_round, status, rz / P.sc.rz0[s]);
       if (rz <= tol2_ref) { status = FEA_SAMPLE_CONVERGED; break; }
       if (refine_round >= kMaxRefine || !(rz < 0.25 * rz_round) || !isfinite(rz)) { status = FEA_SAMPLE_STAGNATED; break; }
       // correction solve: Khat d = r, from d = 0, to the (absolute) refined tolerance
