@@ -399,6 +399,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.sc.cap, b.ns));
   CK(ctx, dalloc(b, &b.sc.rz_mon, b.ns));
   CK(ctx, dalloc(b, &b.sc.rounds, b.ns));
+  CK(ctx, dalloc(b, &b.sc.arrive, 2 * (int64_t)b.ns));
   CK(ctx, dalloc(b, &b.sc.status, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumA, b.ns));
   CK(ctx, dalloc(b, &b.sc.psumB, b.ns));

@@ -57,6 +57,7 @@ struct SysScalars {
   int32_t* iters;
   int32_t* cap;      // iteration budget of the current (re)start; < max_iter only after a reopen
   double* rz_mon;    // true r.r at the previous monitor pass (streaming path)
+  int32_t* arrive;   // [2 ns] arrival counters of the in-kernel second reduction level (p.q / r.r)
   int32_t* rounds;   // extended-precision refinement rounds the system needed (0 for all but ill-conditioned ones)
   int32_t* status;
   double* psumA;     // per-system sums of the CTA partials (two-level mode, huge systems only)
@@ -259,6 +260,33 @@ __device__ __forceinline__ d4 ld_stream_d4(const d4* p) {
 __device__ __forceinline__ d4 ld_nc_d4(const d4* p) {
   d4 v;
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+// L2 eviction policies: the matrix of a system larger than the L2 streams through it once per SpMV and
+// must not push out the vector records that every row gathers (evict_first vs evict_last)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ d4 ld_stream_d4_hint(const d4* p, uint64_t pol) {
+  d4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ d4 ld_nc_d4_hint(const d4* p, uint64_t pol) {
+  d4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i32_hint(const int* p, uint64_t pol) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
 __device__ __forceinline__ int ld_stream_i32(const int* p) {

@@ -25,8 +25,8 @@
 // partials of its own system in a fixed order (a few dozen L2-resident doubles).  Results are
 // therefore bitwise reproducible and independent of which other systems share the batch or the
 // GPU.  Systems owning more than kDirectSumMax CTAs (the ~1M-DOF single solves) get their partials
-// pre-summed by a one-CTA-per-system kernel between the two (two-level mode).  Finished systems
-// cost one flag read per CTA.
+// pre-summed by whichever of their CTAs finishes last (two-level mode, presum_if_last).  Finished
+// systems cost one flag read per CTA.
 #include <cstdio>
 #include <cstdlib>
 
@@ -55,6 +55,35 @@ __device__ __forceinline__ double cta_sum(double v, double* sm /*[kT/32]*/) {
   return t;
 }
 
+// Two-level mode (systems owning more than kDirectSumMax CTAs): the CTA of the system that finishes LAST
+// (arrival counter) pre-sums the system's partials for the next kernel, in the same fixed order whichever
+// CTA that is -- partial i goes to thread i mod kT, then the CTA sum -- so the result has the same bits in
+// every run.  Replaces a separate one-CTA-per-system kernel between the two solver kernels (two launches
+// per iteration of a ~1 M-DOF solve).
+__device__ __forceinline__ void presum_if_last(const double* __restrict__ part, int first, int n, int32_t* arrive,
+                                               double* psum, double* sm /*[kT/32]*/) {
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    __threadfence();                       // this CTA's partial is visible before it is counted
+    last = atomicAdd(arrive, 1) == n - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();                         // the other CTAs' partials are visible after the count was read
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kT) acc += __ldcg(part + first + i);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kT / 32; ++w) t += sm[w];
+    *psum = t;
+    *arrive = 0;                           // ready for the next kernel of this kind
+  }
+}
+
 // Ordered sum of n partials, identical in every lane of every warp that calls it.
 __device__ __forceinline__ double sum_partials(const double* __restrict__ part, int n) {
   double acc = 0.0;
@@ -66,7 +95,9 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
 // U = entries whose loads are issued together before any of them is consumed (memory-level
 // parallelism per thread); MINB = minimum resident CTAs per SM asked of the register allocator.
 // Grid = any size >= P.n_active (the host picks a size class from a slightly stale count).
-template <int U, int MINB>
+// HINT: L2 eviction policies on the loads (matrix evict_first, gathered records evict_last) for systems
+// whose matrix does not fit the L2.
+template <int U, int MINB, bool HINT = false>
 __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict__ Pp, int parity) {
   __shared__ double sm[kT / 32];
   const PcgPtrs& P = *Pp;
@@ -101,8 +132,9 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
   const d4* __restrict__ vt = P.val + base + lane;
   const int32_t* __restrict__ cp = P.col + base + lane;
   const d4* __restrict__ rp = P.rp;
+  const uint64_t pol_m = HINT ? l2_policy_evict_first() : 0, pol_v = HINT ? l2_policy_evict_last() : 0;
   // own row: p_i and the diagonal block [[1, a], [a, 1]]
-  const d4 own = ld_nc_d4(rp + row);
+  const d4 own = HINT ? ld_nc_d4_hint(rp + row, pol_v) : ld_nc_d4(rp + row);
   const double dc = __ldg(P.dcoup + row);
   const double2 pn = make_double2(fma(beta, own.z, own.x), fma(beta, own.w, own.y));
   double a0 = fma(dc, pn.y, pn.x), a1 = fma(dc, pn.x, pn.y);
@@ -111,14 +143,15 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
     int c[U];
     d4 k[U], g[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) c[u] = (j0 + u < L) ? ld_stream_i32(cp + (j0 + u) * 32) : (int)row;
+    for (int u = 0; u < U; ++u)
+      c[u] = (j0 + u < L) ? (HINT ? ld_stream_i32_hint(cp + (j0 + u) * 32, pol_m) : ld_stream_i32(cp + (j0 + u) * 32)) : (int)row;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       k[u].x = k[u].y = k[u].z = k[u].w = 0.0;
-      if (j0 + u < L) k[u] = ld_stream_d4(vt + (j0 + u) * 32);
+      if (j0 + u < L) k[u] = HINT ? ld_stream_d4_hint(vt + (j0 + u) * 32, pol_m) : ld_stream_d4(vt + (j0 + u) * 32);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) g[u] = ld_nc_d4(rp + c[u]);
+    for (int u = 0; u < U; ++u) g[u] = HINT ? ld_nc_d4_hint(rp + c[u], pol_v) : ld_nc_d4(rp + c[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const double px = fma(beta, g[u].z, g[u].x);
@@ -132,6 +165,7 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
   P.q[row] = make_double2(a0, a1);
   const double part = cta_sum(fma(pn.x, a0, pn.y * a1), sm);
   if (threadIdx.x == 0) P.partA[cta] = part;
+  if (P.two_level) presum_if_last(P.partA, first, w.w, P.sc.arrive + 2 * s, P.sc.psumA + s, sm);
 }
 
 typedef void (*spmv_fn)(const PcgPtrs*, int);
@@ -139,7 +173,14 @@ static spmv_fn pick_spmv(int variant) {
   switch (variant) {  // "spmv_variant" option = 100 * U + MINB (tuning knob; measured on B200: 116 best)
     case 112: return k_pcg_spmv<1, 12>;
     case 216: return k_pcg_spmv<2, 16>;
+    case 212: return k_pcg_spmv<2, 12>;
     case 210: return k_pcg_spmv<2, 10>;
+    case 408: return k_pcg_spmv<4, 8>;
+    case 406: return k_pcg_spmv<4, 6>;
+    case 308: return k_pcg_spmv<3, 8>;
+    case 1116: return k_pcg_spmv<1, 16, true>;
+    case 1212: return k_pcg_spmv<2, 12, true>;
+    case 1408: return k_pcg_spmv<4, 8, true>;
     default: return k_pcg_spmv<1, 16>;
   }
 }
@@ -181,6 +222,7 @@ __global__ void __launch_bounds__(kT) k_pcg_update(const PcgPtrs* __restrict__ P
     P.partB[cta] = part;
     if (leader) P.sc.iters[s] += 1;
   }
+  if (P.two_level) presum_if_last(P.partB, first, w.w, P.sc.arrive + 2 * s + 1, P.sc.psumB + s, sm);
 }
 
 // Residual replacement.  The recursion r -= alpha q drifts away from b - K x by rounding (the gap
@@ -289,23 +331,6 @@ __global__ void k_pcg_refine_scalars(const PcgPtrs* __restrict__ Pp, int32_t* __
     P.sc.done[s] = 0;
     atomicSub(P.sc.n_done, 1);
     atomicAdd(n_reopened, 1);
-  }
-}
-
-// two-level mode: one CTA per system pre-sums that system's partials in a fixed order
-__global__ void __launch_bounds__(kT) k_reduce_partials(const PcgPtrs* __restrict__ Pp, int which) {
-  __shared__ double sm[kT / 32];
-  const PcgPtrs& P = *Pp;
-  const double* __restrict__ part = which ? P.partB : P.partA;
-  double* psum = which ? P.sc.psumB : P.sc.psumA;
-  for (int s = blockIdx.x; s < P.ns; s += gridDim.x) {
-    if (P.sc.done[s]) continue;
-    const int first = P.cta_first[s], n = P.cta_count[s];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += kT) acc += __ldg(part + first + i);
-    const double t = cta_sum(acc, sm);
-    if (threadIdx.x == 0) psum[s] = t;
-    __syncthreads();
   }
 }
 
@@ -436,13 +461,10 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   return P;
 }
 
-// one iteration (2 kernels, 4 in two-level mode) on a grid of g CTAs
-static void launch_iteration(Ctx& c, const PcgPtrs* dP, int g, int parity, bool two_level, int ns, cudaStream_t st) {
-  const int gr = ns < 1024 ? ns : 1024;
-  pick_spmv(c.spmv_variant)<<<g, kT, 0, st>>>(dP, parity);
-  if (two_level) k_reduce_partials<<<gr, kT, 0, st>>>(dP, 0);
+// one iteration = two kernels on a grid of g CTAs
+static void launch_iteration(Ctx& c, const PcgPtrs* dP, int g, int parity, cudaStream_t st, int variant) {
+  pick_spmv(variant)<<<g, kT, 0, st>>>(dP, parity);
   k_pcg_update<<<g, kT, 0, st>>>(dP, parity);
-  if (two_level) k_reduce_partials<<<gr, kT, 0, st>>>(dP, 1);
 }
 
 // grid size classes: 148 * 2^(j/2), so a stale count costs at most ~41% idle CTAs
@@ -453,14 +475,14 @@ static int grid_class(int n_active, int ncta) {
   return gi < ncta ? gi : ncta;
 }
 
-static cudaError_t get_chunk_graph(Ctx& c, const PcgPtrs* dP, int g, bool two_level, int ns, cudaGraphExec_t* out) {
-  const int64_t key = ((int64_t)g << 32) | ((int64_t)(two_level ? (ns < 1024 ? ns : 1024) : 0) << 1) | (two_level ? 1 : 0);
+static cudaError_t get_chunk_graph(Ctx& c, const PcgPtrs* dP, int g, int variant, cudaGraphExec_t* out) {
+  const int64_t key = ((int64_t)g << 32) | (int64_t)(uint32_t)variant;   // the SpMV variant is baked into the kernel nodes
   auto it = c.pcg_graphs.find(key);
   if (it != c.pcg_graphs.end()) { *out = it->second; return cudaSuccess; }
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) return e;
-  for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, two_level, ns, c.stream);
+  for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, c.stream, variant);
   k_compact_active<<<1, 1024, 0, c.stream>>>((PcgPtrs*)dP);
   e = cudaStreamEndCapture(c.stream, &graph);
   if (e != cudaSuccess) return e;
@@ -496,8 +518,10 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     if (c.pcg_path != 0 || !codes_fit || (P.cl_cnt[k] && pcg_cluster_capacity(c, k) <= 0)) P.cl_cnt[k] = 0;
     n_cluster += P.cl_cnt[k];
   }
-  const bool two = P.two_level != 0;
-  const int per_iter = two ? 4 : 2;
+  const int per_iter = 2;
+  // L2 eviction hints (matrix evict_first, gathered records evict_last) when the matrix does not fit the L2
+  int variant = c.spmv_variant;
+  if (variant == 0 && (int64_t)b.n_blocks * 36 > (int64_t)96 << 20) variant = 1116;
   int64_t launches = 0;
   cudaError_t e;
   b.stats = fea_solve_stats{};
@@ -506,6 +530,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   if ((e = cudaEventRecord(c.ev_t0, st)) != cudaSuccess) return e;
   k_store_params<<<1, 32, 0, st>>>(P, dP);
   cudaMemsetAsync(b.sc.n_done, 0, sizeof(int32_t), st);
+  cudaMemsetAsync(b.sc.arrive, 0, sizeof(int32_t) * 2 * b.ns, st);
   if (ncta) k_pcg_init_vectors<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
@@ -575,20 +600,18 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     for (; k < k_end; ++k) {
       const int g = grid_class(n_active, ncta);
       cudaGraphExec_t exec = nullptr;
-      if (c.use_graphs && (e = get_chunk_graph(c, dP, g, two, b.ns, &exec)) != cudaSuccess) return e;
+      if (c.use_graphs && (e = get_chunk_graph(c, dP, g, variant, &exec)) != cudaSuccess) return e;
       const bool t = timed < kMaxTimed;
       if (t) cudaEventRecord(c.events[3 * timed], st);
-      pick_spmv(c.spmv_variant)<<<g, kT, 0, st>>>(dP, 0);
-      if (two) k_reduce_partials<<<b.ns < 1024 ? b.ns : 1024, kT, 0, st>>>(dP, 0);
+      pick_spmv(variant)<<<g, kT, 0, st>>>(dP, 0);
       if (t) cudaEventRecord(c.events[3 * timed + 1], st);
       k_pcg_update<<<g, kT, 0, st>>>(dP, 0);
-      if (two) k_reduce_partials<<<b.ns < 1024 ? b.ns : 1024, kT, 0, st>>>(dP, 1);
       if (t) { cudaEventRecord(c.events[3 * timed + 2], st); ++timed; }
-      launch_iteration(c, dP, g, 1, two, b.ns, st);
+      launch_iteration(c, dP, g, 1, st, variant);
       if (exec) {
         if ((e = cudaGraphLaunch(exec, st)) != cudaSuccess) return e;
       } else {
-        for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, two, b.ns, st);
+        for (int i = 2; i < kChunk; ++i) launch_iteration(c, dP, g, i & 1, st, variant);
         k_compact_active<<<1, 1024, 0, st>>>(dP);
       }
       launches += (int64_t)per_iter * kChunk + 1;
@@ -826,6 +849,7 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
   k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc, b.cta_first, b.cta_count, b.partB);
   k_compact_active<<<1, 1024, 0, st>>>(dP);
   k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (d4*)b.rp);
+  cudaMemsetAsync(b.sc.arrive, 0, sizeof(int32_t) * 2 * b.ns, st);
   pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(dP, 0);
   k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, (const double2*)b.q, d_y);
   return cudaGetLastError();
