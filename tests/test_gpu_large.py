@@ -91,3 +91,25 @@ def test_level4_million_dof_solve_properties(ctx):
     # away from the singularity the field has converged: mid-span vertex of the coarse mesh
     mid = int(np.argmin(np.abs(setup.coors[:len(g), 0] - 0.5) + np.abs(setup.coors[:len(g), 1] - 0.5)))
     assert abs(r.u[mid, 1] - g[mid, 1]) <= 0.01 * abs(g[mid, 1])
+
+
+@pytest.mark.parametrize("name,level", [("cantilever", 4), ("gusset", 3)])
+def test_config3_meshes_match_the_stored_sparse_lu_solution(ctx, name, level):
+    """BASELINE config 3 at full size (1.19 M / 1.28 M DOFs; reference applications/cantilever/cantilever.py:26-52,
+    applications/gusset/gusset.py:39-94): the GPU solve against scipy's sparse LU + one refinement step, computed
+    offline (tools/make_c3_reference.py, minutes of CPU) and stored at the coarse mesh's vertices, which keep
+    their indices under uniform refinement (tests/golden/c3_lu.npz)."""
+    import os
+    from fea_diffusion_b200.workload import large_case
+    ref = np.load(os.path.join(cases.ROOT, "tests", "golden", "c3_lu.npz"))
+    setup, n0 = large_case(name, level)
+    with ctx.create_batch(pack([setup.sample])) as b:
+        b.assemble()
+        a, _ = b.sample_sizes()
+        assert int(a[0]) == int(ref["%s_L%d_n_dofs" % (name, level)])
+        r = b.solve(1e-10, 400000).download()
+        st = b.stats()
+    assert r.status[0] == SAMPLE_CONVERGED and st["cluster_systems"] == 0
+    g = ref["%s_L%d_u_coarse" % (name, level)]
+    err = float(np.linalg.norm(r.u[:n0] - g) / np.linalg.norm(g))
+    assert err <= 1e-8, err
