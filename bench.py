@@ -132,6 +132,28 @@ def ncu_traffic(info, name):
     return None
 
 
+def onchip_roofline(sizes, iters, info, launch_ms):
+    """What bounds k_pcg_cluster: the SM's shared-memory / L1TEX data pipe, through which the resident
+    2x2 blocks, the gathered search-direction entries AND the blocks streamed from L2 all return.
+    Bytes through that pipe per launch, from the layout: per stored block 32 B of matrix + 16 B of gathered
+    p + 2 B of gather code; per block row and iteration 16 B own p + 8 B diagonal coupling in the SpMV,
+    16 B p for the iteration's record, 16 B p read + 16 B p written in the x/r/p update.  Peak = measured
+    with tools/smem_bw.cu on a B200 of this pool (profiles/smem_peak.json), conflict-free 128-bit loads."""
+    n_s, nnz_s = sizes
+    rows = n_s / 2.0
+    blocks = nnz_s / 4.0 - rows                    # off-diagonal 2x2 blocks (slice padding ignored)
+    per_iter = blocks * 50.0 + rows * 88.0
+    total = float((iters.astype(np.float64) * per_iter).sum())
+    peak = ncu_field("smem_peak.json", "stream16_GBs")
+    out = {"bound": "shared-memory / L1TEX data pipe", "bytes_per_launch": total,
+           "achieved": total / (launch_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
+           "peak_source": "tools/smem_bw.cu on a B200 of this pool (profiles/smem_peak.json): 148 SMs x 126 B/clk",
+           "bytes_model": "per iteration: 50 B per stored 2x2 block (32 matrix + 16 gathered p + 2 code) + 88 B per block row"}
+    if peak:
+        out["frac"] = out["achieved"] / peak
+    return out
+
+
 # --------------------------------------------------------------------------
 def oracle_unit(job):
     """One plate-condition through the CPU oracle, reference-faithful: assemble, then factor +
@@ -538,6 +560,8 @@ def run_b200(a):
         roofline = {"bound": "hbm", "kernel": "k_pcg_cluster<1..8> (one persistent kernel per cluster size, launched "
                                               "concurrently; most systems ran on %d-CTA clusters)" % cl_size,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "frac_note": "algorithmic bytes vs the HBM peak, ON-CHIP regime: > 1 by design (the matrix crosses HBM once "
+                                 "per solve, not once per iteration); the resource that bounds the kernel is in 'onchip'",
                     "traffic": ncu_traffic(info, "cluster_traffic.json"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms,
                     "timed_launches": len(stats), "pcg_iterations_in_launch": int(res0.iters.sum()),
@@ -546,6 +570,7 @@ def run_b200(a):
                               "exceeds the HBM peak by design; HBM-streaming figures of the same iterations are in "
                               "'streaming_path'",
                     "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"],
+                    "onchip": onchip_roofline(sizes, res0.iters, info, ms),
                     "onchip_pipe": ncu_field("cluster_traffic.json", "onchip_pipe"),
                     "l2_read_peak_gbs": 17900.0, "hbm_read_peak_gbs": 6880.0,
                     "peaks_note": "L2-resident / HBM-resident read bandwidth measured with tools/l2_bw.cu on a B200 of this pool"}

@@ -5,9 +5,10 @@ Same constructor, attributes and methods, same files written (``magnitudes.txt``
 ``materials.txt``, ``ranges.txt``, ``domain.<k>.vtk``, ``regions.vtk``, the PNGs), so
 ``datagen/generate.py`` drives it unchanged.  What differs is where the work happens: the
 reference builds an sfepy ``Problem`` and lets SuperLU / VTK do the arithmetic; here
-``__init__`` restates the region selection on host arrays (``..host.ProblemSetup``),
-``calculate()`` runs assemble + Dirichlet elimination + Jacobi-PCG on the GPU through the C-ABI,
-and the image methods call the CUDA rasteriser.  All load steps come from one solve
+``__init__`` hands the tags, magnitudes and material coordinate lists to the library, which selects
+the regions and derives the Dirichlet mask, material cells, D and the load vector on the device
+(``fea_batch_create_from_conditions``) and assembles the system; ``calculate()`` runs the Jacobi-PCG
+solve through the C-ABI, and the image methods call the CUDA rasteriser.  All load steps come from one solve
 (u_k = t_k * u_final).
 
 One process-wide ``Context`` (GPU 0 unless ``FEA_B200_DEVICE`` says otherwise) is shared by all
@@ -25,12 +26,28 @@ from PIL import Image
 
 from .. import imaging
 from .._capi import SAMPLE_CONVERGED, SAMPLE_EMPTY_ROW
-from ..host import MeshTopology, ProblemSetup, read_mesh
-from ..solver import Context, pack
+from ..host import read_mesh
+from ..solver import Context, PackedConditions, Sample
 from .vtk_io import domain_filename, write_vtk
 
 _shared_context: Optional[Context] = None
-_mesh_cache: Dict[Tuple[str, int, int], Tuple[np.ndarray, np.ndarray, MeshTopology]] = {}
+_mesh_cache: Dict[Tuple[str, int, int], Tuple[np.ndarray, np.ndarray]] = {}
+
+
+class DeviceSetupView:
+    """What ``FEAnalysis.__init__`` derived for one condition, as downloaded from the device: same
+    attributes as ``host.ProblemSetup`` (coors, conn, regions, sample, bbox)."""
+
+    def __init__(self, coors, conn, names, dev):
+        self.coors, self.conn = coors, conn
+        self.regions = {nm: np.flatnonzero(dev.region_flags[0][i]) for i, nm in enumerate(names)}
+        self.region_count = dev.region_count[0]
+        self.sample = Sample(coors=coors, conn=conn, cell_region=dev.cell_region, D=dev.D[0],
+                             fixed=dev.fixed.astype(bool), rhs=dev.rhs)
+
+    def bbox(self):
+        c = self.coors
+        return float(c[:, 0].min()), float(c[:, 1].min()), float(c[:, 0].max()), float(c[:, 1].max())
 
 
 def default_context() -> Context:
@@ -41,14 +58,14 @@ def default_context() -> Context:
 
 
 def _load_mesh(filepath: str):
-    """Mesh arrays + edge topology, cached per (file, mtime, size): every condition of a plate
-    re-opens the same ``part.mesh`` (reference generate.py:88-90)."""
+    """Mesh arrays, cached per (file, mtime, size): every condition of a plate re-opens the same
+    ``part.mesh`` (reference generate.py:88-90)."""
     st = os.stat(filepath)
     key = (path.abspath(filepath), st.st_mtime_ns, st.st_size)
     hit = _mesh_cache.get(key)
     if hit is None:
         coors, conn = read_mesh(filepath)
-        hit = (coors, conn, MeshTopology(conn, len(coors)))
+        hit = (coors, conn)
         if len(_mesh_cache) >= 8:
             _mesh_cache.clear()
         _mesh_cache[key] = hit
@@ -96,20 +113,25 @@ class FEAnalysis:
         self.context = context
         self.rtol, self.max_iter, self.strict = rtol, max_iter, strict
 
-        coors, conn, topology = _load_mesh(path.join(data_dir, filename))
-        self.setup = ProblemSetup(
-            coors, conn,
-            force_vertex_tags_magnitudes=force_vertex_tags_magnitudes,
-            force_edges_tags_magnitudes=force_edges_tags_magnitudes,
-            constraints_vertex_tags=constraints_vertex_tags,
-            constraints_edges_tags=constraints_edges_tags,
-            material_properties_to_vertices=material_properties_to_vertices,
-            youngs_modulus=youngs_modulus, poisson_ratio=poisson_ratio, topology=topology)
+        coors, conn = _load_mesh(path.join(data_dir, filename))
+        kw = dict(force_vertex_tags_magnitudes=force_vertex_tags_magnitudes,
+                  force_edges_tags_magnitudes=force_edges_tags_magnitudes,
+                  constraints_vertex_tags=constraints_vertex_tags, constraints_edges_tags=constraints_edges_tags,
+                  material_properties_to_vertices=material_properties_to_vertices,
+                  youngs_modulus=youngs_modulus, poisson_ratio=poisson_ratio)
+        # region selection, Dirichlet mask, material cells, D and load on the device; the batch (one
+        # sample) stays assembled until calculate()
+        self._packed = PackedConditions([(coors, conn)], [(0, kw)])
+        self._batch = self._ctx().create_batch_from_conditions(self._packed)
+        self._batch.assemble()
+        self.setup = DeviceSetupView(coors, conn, self._packed.names[0], self._batch.setup())
         # side effects of the reference constructor (fea_analysis.py:87-91, 108-115, 278-282)
-        for line in self.setup.magnitudes_lines:
-            self._append_line("magnitudes.txt", line)
-        for line in self.setup.materials_lines:
-            self._append_line("materials.txt", line)
+        from ..dataset import text_lines
+        magnitudes, materials = text_lines(kw, self.setup.region_count)
+        for name, text in (("magnitudes.txt", magnitudes), ("materials.txt", materials)):
+            if text:
+                with open(path.join(self.condition_dir, name), "a+") as f:
+                    f.write(text)
         self.displacement: Optional[np.ndarray] = None   # (num_steps, n_v, 2) after calculate()
         self.cell_strain: Optional[np.ndarray] = None    # (n_cell, 3) final step
         self.cell_stress: Optional[np.ndarray] = None
@@ -133,6 +155,14 @@ class FEAnalysis:
     @property
     def times(self) -> np.ndarray:
         return np.linspace(0.0, 1.0, self.num_steps)
+
+    def __del__(self):
+        b = getattr(self, "_batch", None)
+        if b is not None:
+            try:
+                b.destroy()
+            except Exception:
+                pass
 
     def clear_condition_dir(self):
         for file in os.listdir(self.condition_dir):
@@ -160,13 +190,19 @@ class FEAnalysis:
         """Replaces Problem + Newton + ScipyDirect + SimpleTimeSteppingSolver
         (``fea_analysis.py:418-461``).  Returns False when the final displacement has NaN (the
         reference's only failure signal) or, with ``strict``, when the system is singular."""
-        ctx = self._ctx()
         smp = self.setup.sample
-        with ctx.create_batch(pack([smp])) as b:
-            b.assemble().solve(self.rtol, self.max_iter)
+        b = self._batch
+        if b is None or b.h is None:                 # calculate() called again: set the problem up anew
+            b = self._ctx().create_batch_from_conditions(self._packed)
+            b.assemble()
+        try:
+            b.solve(self.rtol, self.max_iter)
             res = b.download()
             stress_region = 0 if len(smp.D) else -1
             strain, stress = b.cell_strain_stress(stress_region)
+        finally:
+            b.destroy()
+            self._batch = None
         self.status, self.iterations = int(res.status[0]), int(res.iters[0])
         self.relres = float(res.relres[0])
         u = res.u

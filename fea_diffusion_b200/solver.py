@@ -120,30 +120,40 @@ class PackedConditions:
         self.conn = cat([np.asarray(m[1], dtype=np.int32).reshape(-1, k) for m in meshes], np.int32, k)
         self.sample_mesh = np.array([int(m) for m, _ in samples], dtype=np.int32)
         vf_t, vf_m, ef_t, ef_m, vc_t, ec_t, mat_en, mat_xy, dflt = [], [], [], [], [], [], [], [], []
-        n_vf, n_ef, n_vc, n_ec, n_mat = [], [], [], [], []
-        self.names: List[List[str]] = []
+        counts = []
         self.materials: List[List] = []
-        for _, kw in samples:
+        f64 = np.float64
+        for _, kw in samples:      # (kept lean: this loop is the host cost of a batch; numpy converts at the end)
             vf = kw.get("force_vertex_tags_magnitudes") or ()
             ef = kw.get("force_edges_tags_magnitudes") or ()
             vc = kw.get("constraints_vertex_tags") or ()
             ec = kw.get("constraints_edges_tags") or ()
             mats = kw.get("material_properties_to_vertices")
-            items = list(mats.items()) if mats is not None else []
-            vf_t.extend(int(t) for t, _ in vf)
-            vf_m.extend((float(m[0]), float(m[1])) for _, m in vf)
-            ef_t.extend((int(t[0]), int(t[1])) for t, _ in ef)
-            ef_m.extend((float(m[0]), float(m[1])) for _, m in ef)
-            vc_t.extend(int(t) for t in vc)
-            ec_t.extend((int(t[0]), int(t[1])) for t in ec)
-            for (E, nu), pts in items:
-                mat_en.append((float(E), float(nu)))
-                mat_xy.append(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
-            dflt.append((float(kw.get("youngs_modulus", 210000)), float(kw.get("poisson_ratio", 0.3))))
-            n_vf.append(len(vf)); n_ef.append(len(ef)); n_vc.append(len(vc)); n_ec.append(len(ec)); n_mat.append(len(items))
-            self.names.append(["%s%d" % (kind, i) for kind, cnt in zip(self.KINDS, (len(vf), len(ef), len(vc), len(ec), len(items)))
-                               for i in range(cnt)])
-            self.materials.append([key for key, _ in items])
+            for t, m in vf:
+                vf_t.append(t)
+                vf_m.append(m)
+            for t, m in ef:
+                ef_t.append(t)
+                ef_m.append(m)
+            vc_t.extend(vc)
+            ec_t.extend(ec)
+            n_m = 0
+            if mats is not None:
+                keys = list(mats)
+                n_m = len(keys)
+                mat_en.extend(keys)
+                for pts in mats.values():
+                    mat_xy.append(pts if (isinstance(pts, np.ndarray) and pts.dtype == f64 and pts.ndim == 2)
+                                  else np.asarray(pts, dtype=f64).reshape(-1, 2))
+                self.materials.append(keys)
+            else:
+                self.materials.append([])
+            dflt.append((kw.get("youngs_modulus", 210000), kw.get("poisson_ratio", 0.3)))
+            counts.append((len(vf), len(ef), len(vc), len(ec), n_m))
+        cnt = np.asarray(counts, dtype=np.int64).reshape(-1, 5)
+        n_vf, n_ef, n_vc, n_ec, n_mat = (cnt[:, i] for i in range(5))
+        self._counts = cnt
+        self._names = None
 
         def offs(counts):
             return np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
@@ -160,7 +170,7 @@ class PackedConditions:
         self.mat_coord_off = np.concatenate([[0], np.cumsum([len(c) for c in mat_xy])]).astype(np.int64)
         self.mat_coords = cat(mat_xy, np.float64, 2) if mat_xy else np.zeros((0, 2))
         self.default_E_nu = np.asarray(dflt, dtype=np.float64).reshape(-1, 2)
-        self.n_regions = np.array([len(nm) for nm in self.names], dtype=np.int64)
+        self.n_regions = cnt.sum(axis=1)
         nv = mv[self.sample_mesh]
         nc = mc[self.sample_mesh]
         self.vtx_off = np.concatenate([[0], np.cumsum(nv)]).astype(np.int64)
@@ -174,6 +184,14 @@ class PackedConditions:
             vfix_off=ptr(self.vfix_off), vfix_tag=ptr(self.vfix_tag), efix_off=ptr(self.efix_off), efix_tag=ptr(self.efix_tag),
             mat_off=ptr(self.mat_off), mat_E_nu=ptr(self.mat_E_nu), mat_coord_off=ptr(self.mat_coord_off),
             mat_coords=ptr(self.mat_coords), default_E_nu=ptr(self.default_E_nu))
+
+    @property
+    def names(self) -> List[List[str]]:
+        """Region names of every sample, in the order of the device's region rows."""
+        if self._names is None:
+            self._names = [["%s%d" % (kind, i) for kind, c in zip(self.KINDS, row) for i in range(int(c))]
+                           for row in self._counts]
+        return self._names
 
     @property
     def n_vertices(self) -> int:
