@@ -421,6 +421,9 @@ def run_b200(a):
     # batch overlap the bulk of another (fea_diffusion_b200.pipeline.Pipeline) ---------------------
     from fea_diffusion_b200.pipeline import Pipeline
     a.streams = max(1, min(a.streams, a.steps // 2))   # at least two steps per stream, or there is nothing to overlap
+    # the pipeline's host threads hand the GIL to each other between ctypes calls: with the default 5 ms
+    # switch interval a thread that packs the next batch (pure Python + numpy) stalls the launch chain of the others
+    sys.setswitchinterval(float(os.environ.get("FEA_BENCH_SWITCH_INTERVAL", "0.001")))
     pipe = Pipeline(local, a.streams, staggered_priorities=False, first=ctx)
     outs = [BatchResult(u=c.pinned_empty((packed.n_vertices, 2), np.float64), ranges=c.pinned_empty((n, 4), np.float64),
                         iters=c.pinned_empty((n,), np.int32), relres=c.pinned_empty((n,), np.float64),
@@ -460,35 +463,59 @@ def run_b200(a):
         ds_mask = np.array([it.condition == 0 for it in ds_items], np.uint8)
         probe = PackedConditions(ds_meshes, ds_samples)
         n_img = int(probe.n_regions.sum() + ds_mask.sum())
-        arenas = [PinnedArena(c, probe.h2d_bytes + (1 << 20)) for c in pipe.ctxs]
-        ds_outs = [BatchResult(u=c.pinned_empty((probe.n_vertices, 2), np.float64), ranges=c.pinned_empty((n, 4), np.float64),
-                               iters=c.pinned_empty((n,), np.int32), relres=c.pinned_empty((n,), np.float64),
-                               status=c.pinned_empty((n,), np.int32), images=c.pinned_empty((n, 2, ds_size, ds_size), np.uint8))
-                   for c in pipe.ctxs]
-        ds_regs = [c.pinned_empty((n_img, ds_size, ds_size), np.uint8) for c in pipe.ctxs]
-        ds_cls = [None] * len(pipe.ctxs)
-        pack_s = []
+        # Two host threads: a packer turns the condition dicts of the NEXT step into flat pinned arrays while the
+        # GPU thread drives the current one (create -> assemble -> solve -> rasters -> D2H) on one context.  (Dealing
+        # whole steps to several contexts, as the e2e path does, serialises here: the small kernels and copies of
+        # one context's step cannot run while another context's solve has CTAs pending, so every synchronising
+        # call of a step waits for a foreign solve -- measured 55.6 ms per step with 3 contexts, 51 with 2.)
+        import queue
+        arenas = [PinnedArena(ctx, probe.h2d_bytes + (1 << 20)) for _ in range(3)]
+        ds_outs = [BatchResult(u=ctx.pinned_empty((probe.n_vertices, 2), np.float64), ranges=ctx.pinned_empty((n, 4), np.float64),
+                               iters=ctx.pinned_empty((n,), np.int32), relres=ctx.pinned_empty((n,), np.float64),
+                               status=ctx.pinned_empty((n,), np.int32), images=ctx.pinned_empty((n, 2, ds_size, ds_size), np.uint8))]
+        ds_regs = [ctx.pinned_empty((n_img, ds_size, ds_size), np.uint8)]
+        ds_cls = [None]
+        pack_s, phase_s = [], []
 
-        def dataset_step(c, j):
-            k = pipe.ctxs.index(c)
-            t0 = time.perf_counter()
-            arenas[k].reset()
-            pc = PackedConditions(ds_meshes, ds_samples, alloc=arenas[k].empty)
-            pack_s.append(time.perf_counter() - t0)
-            with c.create_batch_from_conditions(pc) as b:
-                b.assemble().solve(a.rtol, a.max_iter).rasterize(ds_size, ds_affine, t1)
-                b.download(images=True, out=ds_outs[k])
-                b.rasterize_regions(ds_mask, out=ds_regs[k])
-                ds_cls[k] = b.classify()
+        def run_dataset(n_steps):
+            q = queue.Queue(maxsize=1)
 
-        pipe.run(list(range(max(a.warmup, a.streams))), dataset_step)
+            def packer():
+                for j in range(n_steps):
+                    t0 = time.perf_counter()
+                    ar = arenas[j % 3]        # in flight at most: one consumed, one queued, one being packed
+                    ar.reset()
+                    pc = PackedConditions(ds_meshes, ds_samples, alloc=ar.empty)
+                    pack_s.append(time.perf_counter() - t0)
+                    q.put(pc)
+
+            th = threading.Thread(target=packer)
+            th.start()
+            for j in range(n_steps):
+                t0 = time.perf_counter()
+                pc = q.get()
+                t1_ = time.perf_counter()
+                with ctx.create_batch_from_conditions(pc) as b:
+                    t2_ = time.perf_counter()
+                    b.assemble().solve(a.rtol, a.max_iter).rasterize(ds_size, ds_affine, t1)
+                    t3_ = time.perf_counter()
+                    b.download(images=True, out=ds_outs[0])
+                    t4_ = time.perf_counter()
+                    b.rasterize_regions(ds_mask, out=ds_regs[0])
+                    ds_cls[0] = b.classify()
+                    t5_ = time.perf_counter()
+                phase_s.append((t1_ - t0, t2_ - t1_, t3_ - t2_, t4_ - t3_, t5_ - t4_, time.perf_counter() - t5_))
+            th.join()
+
         pipe.synchronize()
+        run_dataset(max(a.warmup, 2))
+        ctx.synchronize()
         pack_s.clear()
+        phase_s.clear()
         barrier()
         ctx.event_record(4)
         t0 = time.perf_counter()
-        pipe.run(list(range(a.steps)), dataset_step)
-        pipe.join_into(ctx)
+        run_dataset(a.steps)
         ctx.event_record(5)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -501,7 +528,10 @@ def run_b200(a):
                    "d2h_bytes_per_step": int(o.u.nbytes + o.ranges.nbytes + o.iters.nbytes + o.relres.nbytes + o.status.nbytes
                                              + o.images.nbytes + ds_regs[0].nbytes + 8 * n),
                    "host_pack_ms_per_step": 1e3 * float(np.mean(pack_s)) if pack_s else None,
-                   "streams": a.streams, "timer": "max(wall clock, CUDA events) around %d steps, max over ranks" % a.steps,
+                   "gpu_thread_ms_per_step": dict(zip(("wait_for_packer", "create_from_conditions", "assemble_solve_raster",
+                                                       "download", "region_images_and_classifier", "destroy"),
+                                                       (1e3 * np.mean(phase_s, axis=0)).round(2).tolist())) if phase_s else None,
+                   "host_threads": "1 packer + 1 GPU thread, one context", "timer": "max(wall clock, CUDA events) around %d steps, max over ranks" % a.steps,
                    "region_images_per_step": n_img, "pinned_arena_spills": int(sum(x.spilled for x in arenas)),
                    "classifier": {"well_posed": int(((fl == 0) & (em == 0)).sum()), "floating": int((fl > 0).sum()),
                                   "empty_rows": int((em > 0).sum())},
