@@ -24,14 +24,17 @@ raw = os.path.join(os.path.dirname(os.path.abspath(__file__)), "%s_cluster_ncu_r
 if os.path.exists(raw):
     rows = list(csv.reader(open(raw)))
     hdr = rows[0]
+    kcol = hdr.index("Kernel Name") if "Kernel Name" in hdr else 0
     pipe = {}
     for r in rows[2:]:
-        pipe[re.sub(r"^void\s+|\(.*", "", r[0])] = {
+        pipe[re.sub(r"^void\s+|\(.*", "", r[kcol])] = {
             "l1tex_pct_of_peak_elapsed": float(r[hdr.index("l1tex__throughput.avg.pct_of_peak_sustained_elapsed")]),
             "sm_active_frac": float(r[hdr.index("sm__cycles_active.avg")]) / float(r[hdr.index("sm__cycles_elapsed.avg")]),
-            "issue_active_pct": float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])}
+            "issue_active_pct": float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
+            "shared_wavefronts_pct_of_peak_elapsed": float(r[hdr.index("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")]),
+            "shared_ld_bank_conflict_wavefronts": float(r[hdr.index("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum")]),
+            "shared_wavefronts": float(r[hdr.index("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")])}
     out["onchip_pipe"] = {"per_kernel": pipe, "note": "L1TEX data pipe: pct of peak over the launch; divide by sm_active_frac for the "
-                          "share while the SMs hold a CTA (~66 % for every class = the SpMV share of an iteration: saturated "
-                          "during the SpMV, DESIGN 3.1a)"}
+                          "share while the SMs hold a CTA (DESIGN 3.1a)"}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "cluster_traffic.json"), "w"), indent=1)
 print(json.dumps({k: out[k] for k in ("dram_bytes_per_launch", "l2_bytes_per_launch")}))
