@@ -82,6 +82,9 @@ static_assert(kClU % 4 == 0 && kClUs % 4 == 0, "gather codes are fetched four at
 #define FEA_CL_MONITOR 1024
 #endif
 
+#ifndef FEA_CL_TMEM
+#define FEA_CL_TMEM 1
+#endif
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
@@ -89,6 +92,16 @@ constexpr int kClWords = (kClMax * kClSlices + kClT - 1) / kClT * kClT;   // 32-
 static_assert(kClWords % kClT == 0 && kClSlices <= kClT && kClSlices * 32 <= 4096, "the halo scan handles kClWords / kClT bitmap words per thread");
 constexpr int kClWpt = kClWords / kClT;     // bitmap words per thread (consecutive)
 constexpr int kClTmpBytes = 2 * kClWords * 4 + 128;   // halo bitmap + its prefix sums (set-up only)
+// Tensor memory as a matrix store.  The SM's 256 KB of TMEM is idle in fp64 code; tcgen05.ld.32x32b gives
+// every thread of a warp a private strip of it (lane = thread, column = 32-bit word), which is exactly the
+// shape of a block-SELL slice (one row per lane, one 2x2 block = 8 columns).  Measured (tools/tmem_bw.cu):
+// 456 B/clk/SM into registers, and beside saturating ld.shared traffic both run at 120 B/clk/SM -- TMEM reads
+// do not use the L1TEX data pipe that bounds this kernel, while blocks streamed from L2 do (at 61 B/clk/SM).
+// A warp may only touch the 32 lanes of its quadrant (warp % 4); the warps of a quadrant split the columns.
+constexpr int kTmCols = FEA_CL_TMEM ? 512 / FEA_CL_CTAS_PER_SM : 0;        // columns allocated per CTA (power of two)
+constexpr int kTmWarpCols = FEA_CL_TMEM ? kTmCols / (kClW / 4) / 8 * 8 : 0;  // columns of one warp's strip
+constexpr int kTmWarpBlocks = kTmWarpCols / 8;                               // 2x2 blocks per lane in that strip
+static_assert(kClW % 4 == 0, "TMEM strips are per quadrant of four warps");
 
 struct ClHeader {                 // start of the dynamic shared memory of every CTA
   // one hand-over per iteration: every warp pushes the record (p.q, q.q, r.q, r.r) of its rows to all CTAs;
@@ -111,9 +124,13 @@ struct ClHeader {                 // start of the dynamic shared memory of every
   int32_t fit[kClMax];            // the layout of CTA c fits into its shared memory
   int32_t wsum[kClW];             // block-scan scratch
   int32_t s_halo[kClSlices];      // the slice gathers rows of other CTAs (its warp waits for the halo first)
-  int32_t s_off[kClSlices];       // byte offset of the slice's blocks in the matrix area, -1 = global
+  int32_t s_off[kClSlices];       // byte offset of the slice's other blocks in the matrix area, -1 = global
   int32_t s_len[kClSlices];       // blocks per row of the slice
   int32_t s_aoff[kClSlices];      // entry offset of the slice's gather codes (groups of 4 per lane: [L/4][32][4] u16)
+  int32_t s_nt[kClSlices];        // the first s_nt blocks of every row of the slice live in tensor memory
+  int32_t s_tcol[kClSlices];      // their first column inside the warp's TMEM strip
+  uint32_t tmem_base;             // address of the CTA's TMEM allocation
+  int32_t pad3_;
   int64_t s_base[kClSlices];      // first entry of the slice in the global block-SELL arrays
 #ifdef FEA_CLUSTER_PROFILE
   long long prof[10];
@@ -138,6 +155,54 @@ __device__ __forceinline__ int ld_cluster_s32(uint32_t addr) {
 }
 __device__ __forceinline__ void st_cluster_s32(uint32_t addr, int v) {
   asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ---- tensor memory: 2x2 blocks of one row per lane (8 words per block) ---------------------------------
+// Four (two) blocks of this lane's row and the matching four (two) gathered entries of p, in ONE asm
+// statement: the registers of a tcgen05.ld are valid after tcgen05.wait::ld only, so the wait and the
+// moves into 64-bit registers must not be separable from the load by the compiler's scheduler.  The
+// shared-memory gathers are issued between the load and the wait, i.e. both are in flight together.
+__device__ __forceinline__ void tmem_ld4_gather4(uint32_t taddr, const uint32_t (&ga)[4], d4 (&b)[4], double2 (&p)[4]) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 t<32>;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31}, [%24];\n\t"
+      "ld.shared.v2.f64 {%16,%17}, [%25];\n\t"
+      "ld.shared.v2.f64 {%18,%19}, [%26];\n\t"
+      "ld.shared.v2.f64 {%20,%21}, [%27];\n\t"
+      "ld.shared.v2.f64 {%22,%23}, [%28];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 %0, {t0,t1};\n\t mov.b64 %1, {t2,t3};\n\t mov.b64 %2, {t4,t5};\n\t mov.b64 %3, {t6,t7};\n\t"
+      "mov.b64 %4, {t8,t9};\n\t mov.b64 %5, {t10,t11};\n\t mov.b64 %6, {t12,t13};\n\t mov.b64 %7, {t14,t15};\n\t"
+      "mov.b64 %8, {t16,t17};\n\t mov.b64 %9, {t18,t19};\n\t mov.b64 %10, {t20,t21};\n\t mov.b64 %11, {t22,t23};\n\t"
+      "mov.b64 %12, {t24,t25};\n\t mov.b64 %13, {t26,t27};\n\t mov.b64 %14, {t28,t29};\n\t mov.b64 %15, {t30,t31};\n\t"
+      "}"
+      : "=d"(b[0].x), "=d"(b[0].y), "=d"(b[0].z), "=d"(b[0].w), "=d"(b[1].x), "=d"(b[1].y), "=d"(b[1].z), "=d"(b[1].w),
+        "=d"(b[2].x), "=d"(b[2].y), "=d"(b[2].z), "=d"(b[2].w), "=d"(b[3].x), "=d"(b[3].y), "=d"(b[3].z), "=d"(b[3].w),
+        "=d"(p[0].x), "=d"(p[0].y), "=d"(p[1].x), "=d"(p[1].y), "=d"(p[2].x), "=d"(p[2].y), "=d"(p[3].x), "=d"(p[3].y)
+      : "r"(taddr), "r"(ga[0]), "r"(ga[1]), "r"(ga[2]), "r"(ga[3]));
+}
+__device__ __forceinline__ void tmem_ld2_gather2(uint32_t taddr, uint32_t ga0, uint32_t ga1, d4 (&b)[4], double2 (&p)[4]) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 t<16>;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%12];\n\t"
+      "ld.shared.v2.f64 {%8,%9}, [%13];\n\t"
+      "ld.shared.v2.f64 {%10,%11}, [%14];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 %0, {t0,t1};\n\t mov.b64 %1, {t2,t3};\n\t mov.b64 %2, {t4,t5};\n\t mov.b64 %3, {t6,t7};\n\t"
+      "mov.b64 %4, {t8,t9};\n\t mov.b64 %5, {t10,t11};\n\t mov.b64 %6, {t12,t13};\n\t mov.b64 %7, {t14,t15};\n\t"
+      "}"
+      : "=d"(b[0].x), "=d"(b[0].y), "=d"(b[0].z), "=d"(b[0].w), "=d"(b[1].x), "=d"(b[1].y), "=d"(b[1].z), "=d"(b[1].w),
+        "=d"(p[0].x), "=d"(p[0].y), "=d"(p[1].x), "=d"(p[1].y)
+      : "r"(taddr), "r"(ga0), "r"(ga1));
+}
+__device__ __forceinline__ void tmem_st_block(uint32_t taddr, const d4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__double2loint(b.x)), "r"(__double2hiint(b.x)), "r"(__double2loint(b.y)), "r"(__double2hiint(b.y)),
+               "r"(__double2loint(b.z)), "r"(__double2hiint(b.z)), "r"(__double2loint(b.w)), "r"(__double2hiint(b.w))
+               : "memory");
 }
 
 // ---- synchronisation inside an iteration: transaction barriers, no cluster barrier --------------
@@ -345,6 +410,17 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // (the first cluster.sync() of the queue loop orders the initialisation before any push)
+  uint32_t tm_strip = 0;   // this warp's TMEM strip: lanes of its quadrant, its share of the columns
+  if (kTmCols) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&h->tmem_base)), "n"(kTmCols > 0 ? kTmCols : 32) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tm_strip = h->tmem_base + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)kTmWarpCols;
+  }
 
   for (;;) {
     // ---- next system of the queue (rank 0 pulls, everyone reads it through DSMEM) --------------
@@ -450,9 +526,19 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       h->mat0 = mat0;
       // resident slices: the first slices (round k = 0 of every warp) are resident.  (Measured against
       // giving whole warps resident slices, 48.5 ms, and a warp/round checkerboard, 49.9 ms: 47.2 ms.)
+      // tensor memory first: every warp fills its strip with the leading blocks of its slices (slice i belongs to
+      // warp i % kClW); what is left of a slice goes to shared memory while there is room, else it is streamed
       const int cap = kClSmemBytes - mat0;
+      for (int w = 0; w < kClW; ++w) h->wsum[w] = 0;    // blocks per lane already placed in warp w's strip
       for (int i = 0; i < kClSlices; ++i) {
-        const int bytes = h->s_len[i] * 32 * 32;
+        // a slice that fits takes its blocks in pairs (an odd row length is padded with a zero block); a slice
+        // that does not fit is split at a multiple of four blocks, the granularity of the gather codes
+        const int L = h->s_len[i], used = h->wsum[i % kClW], rem = kTmWarpBlocks - used, Le = (L + 1) & ~1;
+        const int nt = i >= my_sl ? 0 : (Le <= rem ? Le : (rem & ~3));
+        h->s_nt[i] = nt;
+        h->s_tcol[i] = used * 8;
+        h->wsum[i % kClW] = used + nt;
+        const int bytes = max(L - nt, 0) * 32 * 32;
         if (i < my_sl && off + bytes <= cap) { h->s_off[i] = off; off += bytes; }
         else h->s_off[i] = -1;
       }
@@ -529,19 +615,27 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       const int ls = warp + kClW * k;
       if (ls >= my_sl) continue;
       const int off = h->s_off[ls];
-      if (off < 0) continue;
-      const int L = h->s_len[ls];
+      const int L = h->s_len[ls], nt = h->s_nt[ls];
       const int64_t base = h->s_base[ls];
-      // values per slice: L x 32 top halves (k00,k01) then L x 32 bottom halves (k10,k11)
+      const uint32_t tcol = tm_strip + (uint32_t)h->s_tcol[ls];
+      for (int j = 0; j < nt; ++j) {                 // leading blocks: this lane's strip of tensor memory
+        d4 blk;
+        blk.x = blk.y = blk.z = blk.w = 0.0;         // (the pad block of an odd row length)
+        if (j < L) blk = ld_stream_d4(P.val + base + j * 32 + lane);
+        tmem_st_block(tcol + 8u * (uint32_t)j, blk);
+      }
+      if (off < 0 || nt >= L) continue;
+      // values per slice: (L - nt) x 32 top halves (k00,k01) then (L - nt) x 32 bottom halves (k10,k11)
       // (16-byte lane stride: conflict-free 128-bit shared loads)
       double2* st = reinterpret_cast<double2*>(smem + mat0 + off);
-      double2* sb = st + L * 32;
-      for (int j = 0; j < L; ++j) {
+      double2* sb = st + (L - nt) * 32;
+      for (int j = nt; j < L; ++j) {
         const d4 blk = ld_stream_d4(P.val + base + j * 32 + lane);
-        st[j * 32 + lane] = make_double2(blk.x, blk.y);
-        sb[j * 32 + lane] = make_double2(blk.z, blk.w);
+        st[(j - nt) * 32 + lane] = make_double2(blk.x, blk.y);
+        sb[(j - nt) * 32 + lane] = make_double2(blk.z, blk.w);
       }
     }
+    if (kTmCols) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
     // ---- vectors of the thread's rows in registers ----------------------------------------------
     double2 x[kClRpt], r[kClRpt];   // p lives in pbuf (its owner is the only writer)
@@ -641,10 +735,38 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
             mbar_wait(smem_u32(&h->mbarP), (phase >> 2) & 1u);
             halo_here = true;
           }
-          if (off >= 0) {
-            const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane;
-            const double2* sb = st + L * 32;
-            for (int j = 0; j < L; j += kClU) {   // kClU gathers in flight; the tail round is predicated
+          const int nt = kTmCols ? h->s_nt[ls] : 0;
+          if (nt > 0) {   // leading blocks from tensor memory: their own datapath, not the L1TEX pipe
+            const uint32_t tcol = tm_strip + (uint32_t)h->s_tcol[ls];
+            d4 kv[4];
+            double2 pj[4];
+            int j = 0;
+            for (; j + 4 <= nt; j += 4) {
+              const uint2 cc = sa[(j >> 2) * 32];
+              const uint32_t ga[4] = {pbuf_a + 16u * (cc.x & 0xffffu), pbuf_a + 16u * (cc.x >> 16), pbuf_a + 16u * (cc.y & 0xffffu), pbuf_a + 16u * (cc.y >> 16)};
+              tmem_ld4_gather4(tcol + 8u * (uint32_t)j, ga, kv, pj);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
+                a1 = fma(kv[u].z, pj[u].x, a1); a1 = fma(kv[u].w, pj[u].y, a1);
+              }
+            }
+            if (j < nt) {   // a last pair
+              const uint32_t cx = reinterpret_cast<const uint32_t*>(sa + (j >> 2) * 32)[0];
+              tmem_ld2_gather2(tcol + 8u * (uint32_t)j, pbuf_a + 16u * (cx & 0xffffu), pbuf_a + 16u * (cx >> 16), kv, pj);
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                a0 = fma(kv[u].x, pj[u].x, a0); a0 = fma(kv[u].y, pj[u].y, a0);
+                a1 = fma(kv[u].z, pj[u].x, a1); a1 = fma(kv[u].w, pj[u].y, a1);
+              }
+            }
+          }
+          // the other blocks [nt, L) of a split slice (nt is a multiple of four there)
+          if (nt >= L) {
+          } else if (off >= 0) {
+            const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane - nt * 32;
+            const double2* sb = st + (L - nt) * 32;
+            for (int j = nt; j < L; j += kClU) {   // kClU gathers in flight; the tail round is predicated
               uint32_t g[kClU];
               double2 pj[kClU];
 #pragma unroll
@@ -663,9 +785,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
                 }
               }
             }
-          } else {  // blocks that did not fit: streamed from global memory (L2 resident), 4 in flight
+          } else {  // blocks that fit neither: streamed from global memory (L2 resident), 4 in flight
             const d4* vt = P.val + h->s_base[ls] + lane;
-            for (int j = 0; j < L; j += kClUs) {
+            for (int j = nt; j < L; j += kClUs) {
               d4 kv[kClUs];
 #pragma unroll
               for (int u = 0; u < kClUs; ++u) {
@@ -902,6 +1024,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
 #ifdef FEA_CLUSTER_ACCOUNT
   if (tid == 0) atomicAdd(&g_cl_prof[13], (unsigned long long)(clock64() - acc_t0));
 #endif
+  if (kTmCols) {   // every CTA must give its tensor memory back: the next CTA on this SM allocates all of it
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(h->tmem_base), "n"(kTmCols > 0 ? kTmCols : 32) : "memory");
+  }
 }
 
 typedef void (*cluster_fn)(const PcgPtrs*);
