@@ -132,25 +132,38 @@ def ncu_traffic(info, name):
     return None
 
 
-def onchip_roofline(sizes, iters, info, launch_ms):
-    """What bounds k_pcg_cluster: the SM's shared-memory / L1TEX data pipe, through which the resident
-    2x2 blocks, the gathered search-direction entries AND the blocks streamed from L2 all return.
-    Bytes through that pipe per launch, from the layout: per stored block 32 B of matrix + 16 B of gathered
-    p + 2 B of gather code; per block row and iteration 16 B own p + 8 B diagonal coupling in the SpMV,
-    16 B p for the iteration's record, 16 B p read + 16 B p written in the x/r/p update.  Peak = measured
-    with tools/smem_bw.cu on a B200 of this pool (profiles/smem_peak.json), conflict-free 128-bit loads."""
+def onchip_roofline(sizes, iters, stats, launch_ms):
+    """What bounds k_pcg_cluster: the SM's shared-memory / L1TEX data pipe.  Through it return, per iteration,
+    the gathered search-direction entries (16 B per stored 2x2 block), the gather codes (2 B per block), the
+    2x2 blocks that live in shared memory or are streamed from L2 (32 B each) and, per block row, 88 B of
+    vector traffic (own p and diagonal coupling in the SpMV, p for the iteration's record, p read + written in
+    the x/r/p update).  The blocks held in TENSOR MEMORY (tcgen05.ld, 32 B each) use their own datapath and are
+    reported beside it.  Block counts per storage tier come from the kernel's own counters (fea_solve_stats),
+    peaks from tools/smem_bw.cu and tools/tmem_bw.cu on a B200 of this pool (profiles/*_peak.json)."""
     n_s, nnz_s = sizes
     rows = n_s / 2.0
-    blocks = nnz_s / 4.0 - rows                    # off-diagonal 2x2 blocks (slice padding ignored)
-    per_iter = blocks * 50.0 + rows * 88.0
-    total = float((iters.astype(np.float64) * per_iter).sum())
+    rd = {k: float(np.mean([s["cluster_block_reads_" + k] for s in stats])) for k in ("tmem", "smem", "l2")}
+    all_reads = rd["tmem"] + rd["smem"] + rd["l2"]
+    total = 18.0 * all_reads + 32.0 * (rd["smem"] + rd["l2"]) + float((iters.astype(np.float64) * rows * 88.0).sum())
     peak = ncu_field("smem_peak.json", "stream16_GBs")
     out = {"bound": "shared-memory / L1TEX data pipe", "bytes_per_launch": total,
            "achieved": total / (launch_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
            "peak_source": "tools/smem_bw.cu on a B200 of this pool (profiles/smem_peak.json): 148 SMs x 126 B/clk",
-           "bytes_model": "per iteration: 50 B per stored 2x2 block (32 matrix + 16 gathered p + 2 code) + 88 B per block row"}
+           "bytes_model": "per iteration: 18 B per stored 2x2 block (16 gathered p + 2 code) + 32 B per block read from shared "
+                          "memory or L2 + 88 B per block row; block reads counted by the kernel",
+           "block_reads_per_launch": rd,
+           "share_of_blocks": {k: (v / all_reads if all_reads else None) for k, v in rd.items()}}
     if peak:
         out["frac"] = out["achieved"] / peak
+    tm = None
+    try:
+        tm = float(json.load(open(os.path.join(ROOT, "profiles", "tmem_peak.json")))["tmem"]["tmem_GBs"])
+    except Exception:
+        pass
+    out["tensor_memory"] = {"bytes_per_launch": 32.0 * rd["tmem"], "achieved": 32.0 * rd["tmem"] / (launch_ms * 1e-3) / 1e9,
+                            "unit": "GB/s", "peak": tm, "frac": (32.0 * rd["tmem"] / (launch_ms * 1e-3) / 1e9 / tm) if tm else None,
+                            "peak_source": "tools/tmem_bw.cu (profiles/tmem_peak.json): tcgen05.ld.32x32b.x32, 456 B/clk/SM; "
+                                           "beside saturating ld.shared traffic both run at 120 B/clk/SM"}
     return out
 
 
@@ -595,12 +608,12 @@ def run_b200(a):
                     "traffic": ncu_traffic(info, "cluster_traffic.json"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms,
                     "timed_launches": len(stats), "pcg_iterations_in_launch": int(res0.iters.sum()),
-                    "regime": "on-chip: each system's matrix is read from HBM once per solve into the shared memory (and L2) "
-                              "of a thread-block cluster and its CG vectors stay in registers, so achieved algorithmic GB/s "
+                    "regime": "on-chip: each system's matrix is read from HBM once per solve into the tensor memory and shared "
+                              "memory of a thread-block cluster and its CG vectors stay in registers, so achieved algorithmic GB/s "
                               "exceeds the HBM peak by design; HBM-streaming figures of the same iterations are in "
                               "'streaming_path'",
                     "clusters": stats[0]["cluster_count"], "systems_on_chip": stats[0]["cluster_systems"],
-                    "onchip": onchip_roofline(sizes, res0.iters, info, ms),
+                    "onchip": onchip_roofline(sizes, res0.iters, stats, ms),
                     "onchip_pipe": ncu_field("cluster_traffic.json", "onchip_pipe"),
                     "l2_read_peak_gbs": 17900.0, "hbm_read_peak_gbs": 6880.0,
                     "peaks_note": "L2-resident / HBM-resident read bandwidth measured with tools/l2_bw.cu on a B200 of this pool"}

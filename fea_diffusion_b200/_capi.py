@@ -82,6 +82,7 @@ class SolveStats(C.Structure):
         ("cluster_systems", C.c_int32), ("cluster_count", C.c_int32), ("cluster_iterations", C.c_int64),
         ("cluster_ms", C.c_float), ("cluster_size", C.c_int32),
         ("refined_systems", C.c_int32), ("pad_", C.c_int32),
+        ("cluster_block_reads_tmem", C.c_int64), ("cluster_block_reads_smem", C.c_int64), ("cluster_block_reads_l2", C.c_int64),
     ]
 
     def as_dict(self):

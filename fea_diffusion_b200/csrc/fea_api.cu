@@ -130,7 +130,7 @@ cudaError_t api_batch_finish(Batch& b, const int8_t* creg_local, const int32_t* 
   A(dalloc(b, &b.err_flag, 4));
   A(dalloc(b, &b.empty, ns));
   A(dalloc(b, &b.cl_order, ns));
-  A(dalloc(b, &b.cl_counter, 16));  // queue heads of the cluster classes, restart count, scratch
+  A(dalloc(b, &b.cl_counter, 24));  // queue heads of the cluster classes, restart count, scratch
   A(cudaMemcpyAsync(b.d_vtx_off, b.vtx_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(b.d_cell_off, b.cell_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(b.d_reg_off, b.reg_off.data(), sizeof(int32_t) * (ns + 1), cudaMemcpyHostToDevice, st));

@@ -102,7 +102,7 @@ struct Batch {
   int32_t* active_cta = nullptr;     // [NBR/kCtaRows] int4 work list: CTAs of unfinished systems
   int32_t* cl_order = nullptr;       // [ns] systems of the cluster path: class 0 then class 1
   int32_t cl_off[9] = {}, cl_cnt[9] = {};   // index = CTAs per cluster
-  int32_t* cl_counter = nullptr;     // [16] device work-queue heads [1..8], restart count [0], scratch [9], handed back [10]
+  int32_t* cl_counter = nullptr;     // [24] device work-queue heads [1..8], restart count [0], scratch [9], handed back [10], [16..21] three 64-bit block-read counters
   // topology
   int32_t* inc_ptr = nullptr;    // [NV+1] vertex -> stiffness-cell incidence
   int32_t* inc = nullptr;        // entries: cell*4 + local node, ascending

@@ -535,7 +535,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
   if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
-    cudaMemsetAsync(b.cl_counter, 0, 16 * sizeof(int32_t), st);
+    cudaMemsetAsync(b.cl_counter, 0, 24 * sizeof(int32_t), st);
     cudaEventRecord(c.ev_c0, st);
     // one persistent kernel per cluster class, largest clusters first; classes are spread over the
     // main stream and three auxiliary streams so that their clusters are co-scheduled and small
@@ -671,6 +671,11 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     int32_t h_restarts = 0;
     if ((e = cudaMemcpy(&h_restarts, b.cl_counter, sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     b.stats.refined_systems += h_restarts;
+    long long h_reads[3] = {0, 0, 0};
+    if ((e = cudaMemcpy(h_reads, b.cl_counter + 16, sizeof(h_reads), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    b.stats.cluster_block_reads_tmem = h_reads[0];
+    b.stats.cluster_block_reads_smem = h_reads[1];
+    b.stats.cluster_block_reads_l2 = h_reads[2];
 #if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
     pcg_cluster_profile_dump();
 #endif

@@ -85,6 +85,9 @@ static_assert(kClU % 4 == 0 && kClUs % 4 == 0, "gather codes are fetched four at
 #ifndef FEA_CL_TMEM
 #define FEA_CL_TMEM 1
 #endif
+#ifndef FEA_CL_ONE_DIV
+#define FEA_CL_ONE_DIV 0
+#endif
 constexpr int kMonitor = FEA_CL_MONITOR;    // iterations between true-residual monitor passes
 constexpr int kClSlices = kClT / 32 * kClRpt;  // local slices per CTA (64 with 512 threads)
 constexpr int kClSmemBytes = (FEA_CL_CTAS_PER_SM == 1 ? 227 : 113) * 1024;  // dynamic shared memory per CTA
@@ -817,10 +820,13 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       phase ^= 4u;
       if (mode == 0) {
         double s_pq = 0.0, s_qq = 0.0, s_rq = 0.0, s_rr = 0.0;
+        double2 pown[kClRpt];   // this thread's rows of p: read once for the record, kept for the update
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k) {
+          pown[k] = make_double2(0.0, 0.0);
           if (own[k]) {
             const double2 pk = pbuf[tid + kClT * k];
+            pown[k] = pk;
             s_pq = fma(pk.x, q[k].x, fma(pk.y, q[k].y, s_pq));
             s_qq = fma(q[k].x, q[k].x, fma(q[k].y, q[k].y, s_qq));
             s_rq = fma(r[k].x, q[k].x, fma(r[k].y, q[k].y, s_rq));
@@ -864,13 +870,21 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           continue;
         }
         if (!(pq > 0.0 && isfinite(pq))) { status = FEA_SAMPLE_BREAKDOWN; break; }
+#if FEA_CL_ONE_DIV
+        // one division: alpha = rz / pq;  beta = |r - alpha q|^2 / rz = 1 + (rz qq / pq - 2 rq) / pq
+        const double ipq = 1.0 / pq;
+        const double alpha = rz * ipq;
+        const double b1 = fma(fma(rz * qq, ipq, -2.0 * rq), ipq, 1.0);
+        const double beta = b1 > 0.0 ? b1 : 0.0;
+#else
         const double alpha = rz / pq;
         const double est = fma(alpha * alpha, qq, fma(-2.0 * alpha, rq, rz));   // |r - alpha q|^2
         const double beta = est > 0.0 ? est / rz : 0.0;
+#endif
 #pragma unroll
         for (int k = 0; k < kClRpt; ++k) {
           if (own[k]) {
-            double2 pk = pbuf[tid + kClT * k];
+            double2 pk = pown[k];
             x[k].x = fma(alpha, pk.x, x[k].x);
             x[k].y = fma(alpha, pk.y, x[k].y);
             r[k].x = fma(-alpha, q[k].x, r[k].x);
@@ -1011,6 +1025,17 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       if (rank == 0) atomicAdd(&g_cl_prof[14], (unsigned long long)iters * CL);
     }
 #endif
+    if (tid == 0) {   // where this CTA read its blocks from (bench: bytes through the shared-memory pipe / TMEM / L2)
+      long long nb[3] = {0, 0, 0};
+      for (int i = 0; i < my_sl; ++i) {
+        const int L = h->s_len[i], nt = min(kTmCols ? h->s_nt[i] : 0, L);
+        nb[0] += 32 * nt;
+        nb[h->s_off[i] >= 0 ? 1 : 2] += 32 * (L - nt);
+      }
+      unsigned long long* cnt = reinterpret_cast<unsigned long long*>(P.cl_counter + 16);
+      for (int i = 0; i < 3; ++i)
+        if (nb[i]) atomicAdd(cnt + i, (unsigned long long)(nb[i] * (long long)(iters + 1 + refine_round)));
+    }
     if (rank == 0 && tid == 0) {
       P.sc.iters[s] = iters;
       P.sc.status[s] = status;

@@ -37,7 +37,8 @@ struct PcgPtrs {
   int32_t cl_off[9];        // first entry of each class in cl_order (index = CTAs per cluster)
   int32_t cl_cnt[9];        // entries of each class (0 = class not launched)
   int32_t* cl_counter;      // [1..8] work-queue heads, [0] restarts, [10] systems handed back to the
-                            // streaming kernels (device counters, zeroed per solve)
+                            // streaming kernels (device counters, zeroed per solve); [16..21] three 64-bit
+                            // counters: block reads from tensor memory / shared memory / L2
   int32_t cl_halo_cap;      // largest halo (rows gathered from other CTAs) a CTA accepts (test knob)
   // extended-precision refinement of the on-chip path (k_pcg_cluster.cu, dd_residual_rows)
   int32_t refine_dd;        // 1 = systems that hit the fp64 floor get double-double refinement rounds

@@ -166,6 +166,11 @@ typedef struct fea_solve_stats {
    * extended-precision refinement rounds (on-chip path) / restarts from the true residual (streaming) */
   int32_t refined_systems;
   int32_t pad_;
+  /* where the on-chip path read its 2x2 blocks from: sum over its systems of iterations x blocks held in
+   * tensor memory / in shared memory / streamed from L2 (32 bytes per block and iteration each) */
+  int64_t cluster_block_reads_tmem;
+  int64_t cluster_block_reads_smem;
+  int64_t cluster_block_reads_l2;
 } fea_solve_stats;
 
 /* ---- library / context -------------------------------------------------- */

@@ -155,6 +155,58 @@ def element_stiffness(coors: np.ndarray, conn: np.ndarray, D: np.ndarray) -> np.
 
 
 # --------------------------------------------------------------------------
+# strain / stress post-process hook  (fea_analysis.py:397-416)
+# --------------------------------------------------------------------------
+def cell_strain_stress(coors: np.ndarray, conn: np.ndarray, u: np.ndarray, D: np.ndarray
+                       ) -> Tuple[np.ndarray, np.ndarray]:
+    """``calculate_stress_strain`` (``fea_analysis.py:397-416``): the post-process hook evaluates
+    ``ev_cauchy_strain.2.Omega(u)`` and ``ev_cauchy_stress.2.Omega(m.D, u)`` in ``mode='el_avg'``,
+    i.e. per cell (integral over the cell) / (cell volume), strain in sfepy's symmetric-storage order
+    (e11, e22, 2 e12) and stress = D strain.  ``u`` is (n_v,2); ``D`` is (3,3) -- the ONE material the
+    hook names ``m``: every region's material is created under the name ``m`` (``:286-290``) and the
+    expression is evaluated over Omega, so the first material's D is applied to every cell (recalled
+    sfepy behaviour, UNPINNED: no artefact of the reference holds these fields for a multi-material
+    plate) -- or (n_cell,3,3) for a per-cell D.
+    P1: B is constant, so the average is B u_e.  Q1 (UNPINNED, F11): 2x2 Gauss average weighted by |J|.
+    Returns (strain (n_cell,3), stress (n_cell,3))."""
+    nc, k = conn.shape
+    D = np.broadcast_to(np.asarray(D, dtype=np.float64), (nc, 3, 3))
+    X = coors[conn]
+    U = np.asarray(u, dtype=np.float64)[conn]          # (nc,k,2)
+    if k == 3:
+        x, y = X[:, :, 0], X[:, :, 1]
+        b = np.stack([y[:, 1] - y[:, 2], y[:, 2] - y[:, 0], y[:, 0] - y[:, 1]], axis=1)
+        c = np.stack([x[:, 2] - x[:, 1], x[:, 0] - x[:, 2], x[:, 1] - x[:, 0]], axis=1)
+        det = x[:, 0] * b[:, 0] + x[:, 1] * b[:, 1] + x[:, 2] * b[:, 2]
+        gx, gy = b / det[:, None], c / det[:, None]
+        strain = np.stack([(gx * U[:, :, 0]).sum(1), (gy * U[:, :, 1]).sum(1),
+                           (gy * U[:, :, 0] + gx * U[:, :, 1]).sum(1)], axis=1)
+    elif k == 4:
+        g = 0.5 / np.sqrt(3.0)
+        pts = [(0.5 - g, 0.5 - g), (0.5 + g, 0.5 - g), (0.5 + g, 0.5 + g), (0.5 - g, 0.5 + g)]
+        acc = np.zeros((nc, 3))
+        vol = np.zeros(nc)
+        for (xi, eta) in pts:
+            dN = np.array([[-(1 - eta), (1 - eta), eta, -eta], [-(1 - xi), -xi, xi, (1 - xi)]])
+            J = np.einsum("ia,eaj->eij", dN, X)
+            det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+            Ji = np.empty_like(J)
+            Ji[:, 0, 0], Ji[:, 0, 1] = J[:, 1, 1] / det, -J[:, 0, 1] / det
+            Ji[:, 1, 0], Ji[:, 1, 1] = -J[:, 1, 0] / det, J[:, 0, 0] / det
+            G = np.einsum("eij,ja->eia", Ji, dN)
+            w = 0.25 * np.abs(det)
+            e = np.stack([(G[:, 0] * U[:, :, 0]).sum(1), (G[:, 1] * U[:, :, 1]).sum(1),
+                          (G[:, 1] * U[:, :, 0] + G[:, 0] * U[:, :, 1]).sum(1)], axis=1)
+            acc += w[:, None] * e
+            vol += w
+        strain = acc / vol[:, None]
+    else:
+        raise ValueError("cells must be triangles or quads")
+    stress = np.einsum("eij,ej->ei", D, strain)
+    return strain, stress
+
+
+# --------------------------------------------------------------------------
 # assembly  (A-9 .. A-11)
 # --------------------------------------------------------------------------
 def equation_map(fixed_vertex: np.ndarray) -> Tuple[np.ndarray, int]:
@@ -354,6 +406,12 @@ class OracleProblem:
     def solve(self, mode: str = "reference") -> np.ndarray:
         return solve_load_steps(self.stiffness(), self.rhs_final(), self.fixed_vertex,
                                 self.num_steps, mode=mode)
+
+    def strain_stress(self, u_final: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Final-step ``cauchy_strain`` / ``cauchy_stress`` cell fields of ``domain.<k>.vtk``
+        (``fea_analysis.py:397-416``): the hook's ``m.D`` is the first material (see
+        ``cell_strain_stress``); step k's fields are t_k times these (F5)."""
+        return cell_strain_stress(self.coors, self.conn, u_final, self.D[0])
 
     def ranges_lines(self, u_steps: np.ndarray) -> List[str]:
         """``ranges.txt`` lines (custom_plotter.py:181-188, A-17): x_1, y_1, x_2, ..."""

@@ -116,6 +116,31 @@ def test_solve_matches_golden(built, name):
 
 
 @pytest.mark.parametrize("name", list(CASES))
+def test_cell_strain_stress_matches_oracle(built, name):
+    """The post-process hook's cauchy_strain / cauchy_stress cell fields (fea_analysis.py:397-416)
+    against oracle.cell_strain_stress: with the oracle's own displacement the two agree to rounding
+    (1e-12 of the field's largest entry); with the GPU solve to the solver tolerance.  Covers the
+    two-material composite plate (the hook applies the FIRST material's D to every cell) and Q1 cells.
+    UNPINNED in the reference (no artefact holds these fields), stated in the oracle."""
+    setup, orc, b = built[name]
+    r = b.solve(RTOL_SOLVER, 40000).download()
+    region = 0 if len(setup.sample.D) else -1
+    strain, stress = b.cell_strain_stress(region)
+    e_ref, s_ref = orc.strain_stress(r.u)              # same u: isolates the hook's arithmetic
+    assert np.abs(strain - e_ref).max() <= 1e-12 * np.abs(e_ref).max()
+    assert np.abs(stress - s_ref).max() <= 1e-12 * np.abs(s_ref).max()
+    e_or, s_or = orc.strain_stress(orc.solve("best")[-1])   # end to end against the direct solve
+    assert rel(strain, e_or) <= 1e-7 and rel(stress, s_or) <= 1e-7
+    if name == "composite":   # per-cell D (stress_region -1) differs from the hook's single-material rule
+        _, s_cell = b.cell_strain_stress(-1)
+        Dc = orc.D[np.maximum(orc.cell_region, 0)]
+        ref = np.einsum("eij,ej->ei", Dc, e_ref)
+        ref[orc.cell_region < 0] = 0.0
+        assert np.abs(s_cell - ref).max() <= 1e-12 * np.abs(ref).max()
+        assert np.abs(s_cell - stress).max() > 1e-3 * np.abs(stress).max()
+
+
+@pytest.mark.parametrize("name", list(CASES))
 def test_solve_matches_oracle_and_ranges(built, name):
     setup, orc, b = built[name]
     assert orc.classify()["well_posed"] == 1

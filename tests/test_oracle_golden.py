@@ -188,3 +188,16 @@ def test_composite_dataset_images_pin_window_crop_and_region_renders(golden):
         assert ref.shape == mine.shape == (512, 512)
         assert (ref == mine).mean() >= 0.994, name
         assert ((ref < 128) == (mine < 128)).mean() >= 0.996, name
+
+
+def test_strain_stress_oracle_linear_field():
+    """oracle.cell_strain_stress (fea_analysis.py:397-416): a linear displacement u = A x has the
+    constant strain (A00, A11, A01 + A10) in every P1 and Q1 cell, and stress = D strain."""
+    import cases
+    from oracle.fea_oracle import cell_strain_stress
+    A = np.array([[0.3, -0.2], [0.5, 0.1]])
+    for fn in (cases.cantilever, cases.quad_plate):
+        _, orc = fn()
+        e, s = cell_strain_stress(orc.coors, orc.conn, orc.coors @ A.T, orc.D[0])
+        assert np.abs(e - np.array([0.3, 0.1, 0.3])).max() <= 1e-12
+        assert np.abs(s - np.array([0.3, 0.1, 0.3]) @ orc.D[0].T).max() <= 1e-12 * np.abs(s).max()
