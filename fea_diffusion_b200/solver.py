@@ -327,14 +327,16 @@ class Context:
         return int(n.value)
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
-        """numpy array over page-locked host memory (fea_host_alloc); released by close()."""
+        """numpy array over page-locked host memory (fea_host_alloc); released by close() -- the array
+        must not be used after that; garbage collection alone never frees it under a live array."""
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         p = C.c_void_p()
         self._check(self.lib.fea_host_alloc(self.h, count * dtype.itemsize, C.byref(p)))
         self._pinned.append(p)
         buf = (C.c_char * max(count * dtype.itemsize, 1)).from_address(p.value)
-        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        buf._owner = self      # the array's base keeps the context (and with it the allocation) alive until
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)   # close() is called explicitly
 
     def rasterize_fields(self, coors: np.ndarray, conn: np.ndarray, fields: np.ndarray, clim: np.ndarray,
                          affine: np.ndarray, size: int, cell_fields: bool = False) -> np.ndarray:
