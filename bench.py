@@ -364,14 +364,15 @@ def run_b200(a):
             items, rejected, extras = pickle.load(f)
     else:
         items, rejected, extras = build_workload(a.plates, a.conditions, a.image_size, seed0=seed0,
-                                                 extra_as_sampled=a.conditions)
+                                                 extra_as_sampled=a.conditions, workers=os.cpu_count() or 1)
         if cache and rank == 0:
             with open(cache, "wb") as f:
                 pickle.dump((items, rejected, extras), f)
     # dataset_e2e at N > 1: every rank synthesises its OWN plates (the dataset is sharded, not replicated)
     ds_items = items
     if world > 1 and rank > 0 and not a.distinct_shards and "dataset" not in skip:
-        ds_items, _ = build_workload(a.plates, a.conditions, a.image_size, seed0=weak_scaling_seed(a.seed, rank))
+        ds_items, _ = build_workload(a.plates, a.conditions, a.image_size, seed0=weak_scaling_seed(a.seed, rank),
+                                     workers=max(1, (os.cpu_count() or 1) // world))
     t_gen = time.perf_counter() - t_gen
     n = len(items)
     ctx = Context(local)
@@ -584,7 +585,9 @@ def run_b200(a):
                       "classifier": {"well_posed": int(wp.sum()), "floating_parts": int((fl > 0).sum()), "empty_rows": int((em > 0).sum())},
                       "well_posed_not_converged": int((wp & (r_as.status != 0)).sum()),
                       "ill_posed_reported_converged": int((~wp & (r_as.status == 0)).sum()),
-                      "note": "conditions exactly as the sampler draws them; the reference writes SuperLU noise for the singular ones"}
+                      "note": "conditions exactly as the sampler draws them, material regions by the reference's own methods "
+                              "(KMeans over flattened centres / agglomerative, scikit-learn); the reference writes SuperLU noise "
+                              "for the singular ones"}
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
     # Plate-sized systems are solved on chip (k_pcg_cluster: one system per thread-block cluster,

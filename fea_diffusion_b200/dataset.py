@@ -52,9 +52,9 @@ MAX_DRAWS = 400      # per plate, like workload.plate_conditions
 def _plate_job(args):
     """(worker process) mesh of one plate + candidate conditions ``skip .. skip + count - 1`` of its
     sampler stream (one ``sample_conditions`` call per candidate, so that the stream can be resumed)."""
-    plate, seed, image_size, mesh_size, skip, count = args
+    plate, seed, image_size, mesh_size, skip, count, region_method = args
     t0 = time.perf_counter()
-    gen, ptags, ltags = make_plate(seed + plate, mesh_size)
+    gen, ptags, ltags = make_plate(seed + plate, mesh_size, region_method=region_method)
     coors, conn = gen.mesh
     cands = []
     for k in range(skip + count):
@@ -151,9 +151,11 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
                      writer_threads: int = 8, save_meshes: bool = False, well_posed: bool = True,
                      start_plate: int = 0, rtol: float = 1e-10, max_iter: int = 50000,
                      save_displacement: bool = True, save_stress: bool = False, save_strain: bool = False,
-                     progress: Optional[Callable[[int, int], None]] = None) -> Dict:
+                     progress: Optional[Callable[[int, int], None]] = None, region_method: str = "reference") -> Dict:
     """Generates the plates ``start_plate .. num_plates-1`` owned by ``rank`` of ``world`` into
-    ``data_dir``.  Returns throughput statistics."""
+    ``data_dir``.  Returns throughput statistics.  ``region_method``: how the condition sampler draws the
+    material regions -- ``"reference"`` = the reference's KMeans / agglomerative methods (scikit-learn,
+    ``mesh_generator.py:319-385``), ``"lloyd"`` = the fast stand-in of the benchmark workloads."""
     assert num_steps > 1, "Must have at least 2 steps per condition."
     os.makedirs(data_dir, exist_ok=True)
     mine = plate_shard(num_plates - start_plate, rank, world, start=start_plate)
@@ -267,7 +269,8 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
                     j = jobs[ji]
                     if len(j["cands"]) >= MAX_DRAWS:
                         raise RuntimeError("plate %d: no usable condition in %d draws" % (j["plate"], MAX_DRAWS))
-                    args.append((j["plate"], seed, image_size, mesh_size, len(j["cands"]), 2 * FIRST_DRAWS * conditions_per_plate))
+                    args.append((j["plate"], seed, image_size, mesh_size, len(j["cands"]), 2 * FIRST_DRAWS * conditions_per_plate,
+                                 region_method))
                 stats["extra_draw_jobs"] += len(args)
                 for ji, more in zip(short, pool.map(_plate_job, args)):
                     jobs[ji]["cands"].extend(more["cands"])
@@ -279,7 +282,7 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
         stats["batches"] += 1
 
     first = FIRST_DRAWS * conditions_per_plate
-    jobs_args = [(p, seed, image_size, mesh_size, 0, first) for p in mine]
+    jobs_args = [(p, seed, image_size, mesh_size, 0, first, region_method) for p in mine]
     ctx = None
     with ThreadPoolExecutor(max_workers=writer_threads) as writers:
         with mp.get_context("fork").Pool(workers) as pool:   # forked BEFORE the CUDA context exists

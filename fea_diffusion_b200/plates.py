@@ -14,9 +14,15 @@ BASELINE.json ("M-plate(seed)"):
   gmsh's frontal mesh at ``mesh_size=1e-2``; geometry points come first so that the 1-based point
   tag equals vertex index + 1 (SURVEY A-6);
 * conditions -- a restatement of ``sample_conditions`` (``:397-521``) driven by one seeded
-  ``random.Random``; material regions are Lloyd clusters of the vertices merged into 1-5 regions
-  (stand-in for the KMeans / agglomerative draw of ``:319-385``), materials from the reference's
-  18-entry table (``:33-55``), forces uniform integers in +-[1, 1000] (``:66, 493-519``).
+  ``random.Random``, in the reference's draw order.  Material regions (``:319-385``), selected by
+  ``region_method``: ``"reference"`` restates the reference's two methods on scikit-learn (KMeans of the
+  vertices into 5-20 clusters merged by a second KMeans over the FLATTENED centres, or agglomerative
+  clustering with complete / average / ward linkage -- quirks included, see ``_regions_kmeans``);
+  ``"lloyd"`` is the fast stand-in the benchmark workloads were defined with in round 1 (Lloyd clusters
+  merged into bands).  The reference draws the method, cluster counts and materials from the UNSEEDED
+  global ``random`` module and leaves KMeans unseeded, so its own runs are not reproducible; here every
+  one of those draws comes from the seeded stream.  Materials from the reference's 18-entry table
+  (``:33-55``), forces uniform integers in +-[1, 1000] (``:66, 493-519``).
 
 Parity is always "same mesh through both paths", so the mesher does not need to match gmsh.
 """
@@ -175,13 +181,17 @@ class PlateGenerator:
     """Seeded stand-in for the reference's ``MeshGenerator`` (same constructor defaults)."""
 
     def __init__(self, num_polygons_range=(1, 3), points_per_polygon_range=(3, 8), holes_per_polygon_range=(0, 3),
-                 points_per_hole_range=(3, 4), num_regions=(1, 5), force_magnitude_range=(1, 1000), random_seed=None):
+                 points_per_hole_range=(3, 4), num_regions=(1, 5), force_magnitude_range=(1, 1000), random_seed=None,
+                 region_method: str = "reference"):
         self.num_polygons_range = num_polygons_range
         self.points_per_polygon_range = points_per_polygon_range
         self.holes_per_polygon_range = holes_per_polygon_range
         self.points_per_hole_range = points_per_hole_range
         self.num_regions = num_regions
         self.force_magnitude_range = force_magnitude_range
+        if region_method not in ("reference", "lloyd"):
+            raise ValueError("region_method must be 'reference' or 'lloyd'")
+        self.region_method = region_method
         self.random = random.Random(random_seed)
         self.np_rng = np.random.default_rng(random_seed)
         self.mesh: Optional[Tuple[np.ndarray, np.ndarray]] = None
@@ -299,8 +309,57 @@ class PlateGenerator:
         self.mesh = (np.ascontiguousarray(pts[used]), np.ascontiguousarray(new[tri].astype(np.int32)))
         return ptags, ltags
 
-    # ---- material regions (stand-in for mesh_generator.py:319-395) -------------
+    # ---- material regions (mesh_generator.py:319-395) --------------------------
     def _create_regions_randomly(self) -> List[np.ndarray]:
+        """``_create_regions_randomly`` (``:379-386``): one of the two clustering methods, drawn first."""
+        if self.region_method == "lloyd":
+            return self._regions_lloyd()
+        method = self.random.choice(["kmeans", "agglomerative"])
+        if method == "kmeans":
+            return self._regions_kmeans()
+        return self._regions_agglomerative(self.random.choice(["complete", "average", "ward"]))
+
+    @staticmethod
+    def _sklearn():
+        try:
+            from sklearn.cluster import AgglomerativeClustering, KMeans
+        except ImportError as e:   # no silent change of the sampled distribution
+            raise ImportError("region_method='reference' needs scikit-learn (the reference's own dependency, "
+                              "mesh_generator.py:16); pass region_method='lloyd' for the stand-in") from e
+        return AgglomerativeClustering, KMeans
+
+    def _regions_kmeans(self) -> List[np.ndarray]:
+        """``_create_regions_with_kmeans`` (``:319-352``).  KMeans of the mesh points (3-D, z = 0, as pyvista
+        reads them) into 5-20 clusters; the clusters are merged into ``num_regions`` regions by a second KMeans
+        that the reference runs on ``cluster_centers_.reshape(-1, 1)`` -- the FLATTENED centres
+        (x0, y0, z0, x1, ...) -- and indexes with the cluster number: cluster i takes the label of scalar i of
+        that list, i.e. of coordinate i % 3 of centre i // 3.  Restated as written."""
+        _, KMeans = self._sklearn()
+        coors = self.mesh[0]
+        pts = np.concatenate([coors, np.zeros((len(coors), 1))], axis=1)
+        n_clusters = self.random.randint(5, 20)
+        km = KMeans(n_clusters=n_clusters, n_init=1, random_state=self.random.randrange(2 ** 31))
+        lab = km.fit_predict(pts)
+        n_regions = self.random.randint(*self.num_regions)
+        km2 = KMeans(n_clusters=n_regions, n_init=1, random_state=self.random.randrange(2 ** 31))
+        lab2 = km2.fit_predict(km.cluster_centers_.reshape(-1, 1))
+        regions: List[List[np.ndarray]] = [[] for _ in range(n_regions)]
+        for i in range(n_clusters):
+            regions[int(lab2[i])].append(coors[lab == i])
+        return [np.concatenate(r) if r else np.zeros((0, 2)) for r in regions]
+
+    def _regions_agglomerative(self, link: str) -> List[np.ndarray]:
+        """``_create_regions_with_agglomerative_clustering`` (``:354-377``): the vertices clustered straight
+        into ``num_regions`` regions."""
+        Agglomerative, _ = self._sklearn()
+        coors = self.mesh[0]
+        pts = np.concatenate([coors, np.zeros((len(coors), 1))], axis=1)
+        n_regions = self.random.randint(*self.num_regions)
+        lab = Agglomerative(n_clusters=n_regions, linkage=link).fit_predict(pts)
+        return [coors[lab == r] for r in range(n_regions)]
+
+    def _regions_lloyd(self) -> List[np.ndarray]:
+        """Stand-in (round-1 benchmark workloads): Lloyd clusters merged into bands along a random direction."""
         coors = self.mesh[0]
         n_clusters = self.random.randint(5, 20)
         n_regions = self.random.randint(*self.num_regions)
@@ -378,9 +437,11 @@ class PlateGenerator:
         return conditions
 
 
-def make_plate(seed: int, mesh_size: float = 1e-2, max_tries: int = 50):
-    """One plate: (generator with .mesh set, ptags, ltags).  Deterministic in ``seed``."""
-    gen = PlateGenerator(random_seed=seed)
+def make_plate(seed: int, mesh_size: float = 1e-2, max_tries: int = 50, region_method: str = "lloyd"):
+    """One plate: (generator with .mesh set, ptags, ltags).  Deterministic in ``seed``.  The benchmark
+    workloads keep the round-1 ``"lloyd"`` regions (their seeds, iteration counts and the ill-conditioned
+    plate the parity tests pin are defined on them); the dataset generator passes ``"reference"``."""
+    gen = PlateGenerator(random_seed=seed, region_method=region_method)
     for _ in range(max_tries):
         try:
             g = gen.normalize_geometry(gen.generate_geometry())

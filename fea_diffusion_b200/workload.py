@@ -25,7 +25,8 @@ class WorkItem:
 
 
 def plate_conditions(seed: int, conditions_per_plate: int, image_size: int, mesh_size: float = 1e-2,
-                     well_posed: bool = True, max_draws: int = 400, extra_as_sampled: int = 0):
+                     well_posed: bool = True, max_draws: int = 400, extra_as_sampled: int = 0,
+                     as_sampled_method: str = "reference"):
     """All conditions of one plate.  With ``well_posed`` the condition sampler is redrawn until
     every stiffness-connected component carries >= 2 fixed vertices and no active vertex is
     isolated (SURVEY A-19); the number of rejected draws is returned for the report."""
@@ -53,20 +54,48 @@ def plate_conditions(seed: int, conditions_per_plate: int, image_size: int, mesh
         # further draws of the same plate exactly as the sampler produces them (the reference's own
         # distribution, a third of it singular by construction): condition dicts only,
         # the device derives everything else (fea_batch_create_from_conditions)
-        extra = [condition_kwargs(c) for c in gen.sample_conditions(ptags, ltags, extra_as_sampled)]
+        # -- with the reference's own region methods (KMeans / agglomerative, plates.py) on the same mesh,
+        # from a sampler stream of their own
+        import copy
+        import random
+        g2 = copy.copy(gen)
+        g2.region_method = as_sampled_method
+        g2.random = random.Random(seed * 7919 + 17)
+        extra = [condition_kwargs(c) for c in g2.sample_conditions(ptags, ltags, extra_as_sampled)]
         return items, rejected, extra
     return items, rejected
 
 
+def _plate_job(a):
+    try:   # one thread per worker process: the pool already uses every core (scikit-learn / BLAS would each take all)
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(1):
+            return plate_conditions(a[0], a[1], a[2], a[3], a[4], extra_as_sampled=a[5])
+    except ImportError:
+        return plate_conditions(a[0], a[1], a[2], a[3], a[4], extra_as_sampled=a[5])
+
+
 def build_workload(n_plates: int, conditions_per_plate: int = 4, image_size: int = 64, seed0: int = 0,
-                   mesh_size: float = 1e-2, well_posed: bool = True, extra_as_sampled: int = 0):
-    """(items, rejected draws[, as-sampled condition kwargs per plate])."""
+                   mesh_size: float = 1e-2, well_posed: bool = True, extra_as_sampled: int = 0, workers: int = 1):
+    """(items, rejected draws[, as-sampled condition kwargs per plate]).  Plates are independent and seeded
+    one by one, so ``workers`` > 1 (a fork pool: call it before the process owns a CUDA context) returns the
+    same workload as the serial loop."""
     items: List[WorkItem] = []
     rejected = 0
     extras = []
-    for p in range(n_plates):
-        r = plate_conditions(seed0 + p, conditions_per_plate, image_size, mesh_size, well_posed,
-                             extra_as_sampled=extra_as_sampled)
+    jobs = [(seed0 + p, conditions_per_plate, image_size, mesh_size, well_posed, extra_as_sampled) for p in range(n_plates)]
+    if workers > 1 and n_plates > 1:
+        import multiprocessing as mp
+        if extra_as_sampled:
+            try:   # imported once here, inherited by the forked workers (seconds per process otherwise)
+                import sklearn.cluster  # noqa: F401
+            except ImportError:
+                pass
+        with mp.get_context("fork").Pool(min(workers, n_plates)) as pool:
+            results = pool.map(_plate_job, jobs, chunksize=1)
+    else:
+        results = [_plate_job(j) for j in jobs]
+    for r in results:
         items.extend(r[0])
         rejected += r[1]
         if extra_as_sampled:

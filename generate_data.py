@@ -46,6 +46,9 @@ def parse(argv=None):
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the plates over (batched).")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--plates_per_batch", type=int, default=50)
+    ap.add_argument("--region_method", choices=["reference", "lloyd"], default="reference",
+                    help="material regions of the condition sampler: the reference's KMeans / agglomerative methods "
+                         "(scikit-learn) or the fast Lloyd stand-in of the benchmark workloads (batched backend)")
     ap.add_argument("--rank", type=int, default=None, help=argparse.SUPPRESS)   # set for the per-GPU children
     return ap.parse_args(argv)
 
@@ -80,7 +83,7 @@ def main(argv=None):
     st = generate_dataset(a.data_dir, a.num_plates, a.conditions_per_plate, a.image_size, a.steps_per_condition,
                           a.mesh_size, seed=a.seed, rank=rank, world=a.gpus, plates_per_batch=a.plates_per_batch,
                           save_meshes=a.save_meshes, start_plate=start, save_displacement=a.save_displacement,
-                          save_stress=a.save_stress, save_strain=a.save_strain,
+                          save_stress=a.save_stress, save_strain=a.save_strain, region_method=a.region_method,
                           progress=lambda d, n: print("rank %d: %d / %d plates" % (rank, d, n), flush=True))
     print(json.dumps(st))
 

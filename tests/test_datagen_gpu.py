@@ -161,7 +161,7 @@ def test_batched_generator_matches_the_dropin_loop_sample_by_sample(tmp_path):
     from fea_diffusion_b200.dataset import generate_dataset
     from fea_diffusion_b200.workload import plate_conditions
     kw = dict(conditions_per_plate=2, image_size=64, num_steps=5, mesh_size=5e-2, seed=7, plates_per_batch=2,
-              workers=2, save_meshes=True, save_stress=True, save_strain=True)
+              workers=2, save_meshes=True, save_stress=True, save_strain=True, region_method="lloyd")   # as plate_conditions
     d1 = str(tmp_path / "one")
     st = generate_dataset(d1, 3, **kw)
     assert st["plates"] == 3 and st["samples"] == 6

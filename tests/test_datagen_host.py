@@ -118,3 +118,53 @@ def test_medit_writer_round_trips_bit_exactly(tmp_path):
     write_medit(str(tmp_path / "q.mesh"), np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]]), np.array([[0, 1, 2, 3]]))
     co, cn = host.read_mesh(str(tmp_path / "q.mesh"))
     assert cn.shape == (1, 4)
+
+
+def test_reference_region_methods_partition_the_vertices_and_are_seeded():
+    """Material regions of the condition sampler by the reference's own methods
+    (mesh_generator.py:319-385, restated on scikit-learn in plates.py): every draw partitions the
+    mesh vertices into 1..5 non-empty regions, both methods and all three linkages occur, the
+    KMeans merge follows the reference's flattened-centre indexing, and a seed reproduces its stream."""
+    pytest.importorskip("sklearn")
+    from sklearn.cluster import KMeans
+    from fea_diffusion_b200.plates import make_plate
+    gen, ptags, ltags = make_plate(3, mesh_size=4e-2, region_method="reference")
+    coors = gen.mesh[0]
+    seen = set()
+    orig_km, orig_ag = gen._regions_kmeans, gen._regions_agglomerative
+    gen._regions_kmeans = lambda: (seen.add("kmeans"), orig_km())[1]
+    gen._regions_agglomerative = lambda link: (seen.add(link), orig_ag(link))[1]
+    conds = gen.sample_conditions(ptags, ltags, 24)
+    assert seen == {"kmeans", "complete", "average", "ward"}
+    for c in conds:
+        regs = list(c["material_regions"].values())
+        assert 1 <= len(regs) <= 5 and all(len(r) for r in regs)
+        allp = np.concatenate(regs)
+        assert len(allp) == len(coors)
+        assert np.array_equal(np.unique(allp, axis=0), np.unique(coors, axis=0))
+    # same seed, same stream
+    gen2, p2, l2 = make_plate(3, mesh_size=4e-2, region_method="reference")
+    c2 = gen2.sample_conditions(p2, l2, 3)
+    for a, b in zip(conds[:3], c2):
+        assert list(a["material_regions"]) == list(b["material_regions"])
+        assert all(np.array_equal(x, y) for x, y in zip(a["material_regions"].values(), b["material_regions"].values()))
+        # (magnitudes are drawn after ALL conditions of a call, mesh_generator.py:493-519: compare the tags)
+        assert [t for t, _ in a["point_forces"]] == [t for t, _ in b["point_forces"]]
+        assert a["edge_constraints"] == b["edge_constraints"]
+    # the merge rule: cluster i takes the label of scalar i of the flattened (x0, y0, z0, x1, ...) centres
+    gen3, _, _ = make_plate(3, mesh_size=4e-2, region_method="reference")
+    state = gen3.random.getstate()
+    regs = gen3._regions_kmeans()
+    gen3.random.setstate(state)
+    pts = np.concatenate([coors, np.zeros((len(coors), 1))], axis=1)
+    nc = gen3.random.randint(5, 20)
+    km = KMeans(n_clusters=nc, n_init=1, random_state=gen3.random.randrange(2 ** 31))
+    lab = km.fit_predict(pts)
+    nr = gen3.random.randint(1, 5)
+    lab2 = KMeans(n_clusters=nr, n_init=1, random_state=gen3.random.randrange(2 ** 31)).fit_predict(km.cluster_centers_.reshape(-1, 1))
+    for r in range(nr):
+        want = np.concatenate([coors[lab == i] for i in range(nc) if lab2[i] == r] or [np.zeros((0, 2))])
+        assert np.array_equal(regs[r], want)
+    # the mesh does not depend on the region method
+    lloyd, _, _ = make_plate(3, mesh_size=4e-2, region_method="lloyd")
+    assert np.array_equal(lloyd.mesh[0], coors) and np.array_equal(lloyd.mesh[1], gen.mesh[1])
