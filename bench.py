@@ -359,7 +359,24 @@ def run_b200(a):
         import pickle
         cache = "%s.%d.%d.%d.%d.pkl" % (cache, a.plates, a.conditions, a.image_size, seed0)
     skip = set(x for x in a.skip.split(",") if x)
-    if cache and os.path.exists(cache):
+    # N > 1 without --distinct-shards: every rank solves the SAME workload, so rank 0 alone generates it (all
+    # cores) and hands it over through a file on the node; the other ranks meanwhile generate the plates of
+    # their own dataset_e2e shard (8 ranks x all-core pools on one box would oversubscribe the host 8x)
+    share = None
+    if world > 1 and not a.distinct_shards and not cache:
+        import pickle
+        share = os.path.join(os.environ.get("TMPDIR", "/tmp"), "fea_bench_workload.%s.%s.pkl"
+                             % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run")))
+    ds_items = None
+    if share and rank > 0:
+        if "dataset" not in skip:
+            ds_items, _ = build_workload(a.plates, a.conditions, a.image_size, seed0=weak_scaling_seed(a.seed, rank),
+                                         workers=max(1, (os.cpu_count() or 1) // world))
+        dist.all_reduce(torch.zeros(1))   # host barrier over gloo (CPU tensor): rank 0 has written the file
+        with open(share, "rb") as f:
+            items, rejected, extras = pickle.load(f)
+        dist.all_reduce(torch.zeros(1))   # everybody has read it: rank 0 removes it
+    elif cache and os.path.exists(cache):
         with open(cache, "rb") as f:
             items, rejected, extras = pickle.load(f)
     else:
@@ -368,11 +385,16 @@ def run_b200(a):
         if cache and rank == 0:
             with open(cache, "wb") as f:
                 pickle.dump((items, rejected, extras), f)
+        if share:
+            with open(share + ".tmp", "wb") as f:
+                pickle.dump((items, rejected, extras), f)
+            os.replace(share + ".tmp", share)
+            dist.all_reduce(torch.zeros(1))
+            dist.all_reduce(torch.zeros(1))
+            os.remove(share)
     # dataset_e2e at N > 1: every rank synthesises its OWN plates (the dataset is sharded, not replicated)
-    ds_items = items
-    if world > 1 and rank > 0 and not a.distinct_shards and "dataset" not in skip:
-        ds_items, _ = build_workload(a.plates, a.conditions, a.image_size, seed0=weak_scaling_seed(a.seed, rank),
-                                     workers=max(1, (os.cpu_count() or 1) // world))
+    if ds_items is None:
+        ds_items = items
     t_gen = time.perf_counter() - t_gen
     n = len(items)
     ctx = Context(local)
@@ -477,75 +499,115 @@ def run_b200(a):
         ds_mask = np.array([it.condition == 0 for it in ds_items], np.uint8)
         probe = PackedConditions(ds_meshes, ds_samples)
         n_img = int(probe.n_regions.sum() + ds_mask.sum())
-        # Two host threads: a packer turns the condition dicts of the NEXT step into flat pinned arrays while the
-        # GPU thread drives the current one (create -> assemble -> solve -> rasters -> D2H) on one context.  (Dealing
-        # whole steps to several contexts, as the e2e path does, serialises here: the small kernels and copies of
-        # one context's step cannot run while another context's solve has CTAs pending, so every synchronising
-        # call of a step waits for a foreign solve -- measured 55.6 ms per step with 3 contexts, 51 with 2.)
+        # Three host threads on one GPU: a packer turns the condition dicts of step j + 1 into flat pinned arrays and
+        # uploads the big ones (coordinates, connectivity, material coordinate lists) on a context of its own; the
+        # compute thread drives step j on the main context (create -> assemble -> solve -> rasters -> region rasters +
+        # classifier staged on the device, fea_batch_stage_outputs); a reader fetches step j - 1 on a second context's
+        # stream (fea_batch_fetch_outputs), so the ~60 MB of D2H copies run on a copy engine under the next solve.
+        # (Dealing whole steps to several contexts, as the e2e path does, serialises here: the small kernels of one
+        # context's step cannot run while another context's solve has CTAs pending, so every synchronising call of a
+        # step waits for a foreign solve -- measured 55.6 ms per step with 3 contexts, 51 with 2, 38.4 with one
+        # context doing everything in turn.)
         import queue
-        arenas = [PinnedArena(ctx, probe.h2d_bytes + (1 << 20)) for _ in range(3)]
+        copy_ctx, up_ctx = Context(local), Context(local)
+        arenas = [PinnedArena(ctx, probe.h2d_bytes + (1 << 20)) for _ in range(4)]
         ds_outs = [BatchResult(u=ctx.pinned_empty((probe.n_vertices, 2), np.float64), ranges=ctx.pinned_empty((n, 4), np.float64),
                                iters=ctx.pinned_empty((n,), np.int32), relres=ctx.pinned_empty((n,), np.float64),
-                               status=ctx.pinned_empty((n,), np.int32), images=ctx.pinned_empty((n, 2, ds_size, ds_size), np.uint8))]
-        ds_regs = [ctx.pinned_empty((n_img, ds_size, ds_size), np.uint8)]
+                               status=ctx.pinned_empty((n,), np.int32), images=ctx.pinned_empty((n, 2, ds_size, ds_size), np.uint8))
+                   for _ in range(2)]
+        ds_regs = [ctx.pinned_empty((n_img, ds_size, ds_size), np.uint8) for _ in range(2)]
         ds_cls = [None]
-        pack_s, phase_s = [], []
+        pack_s, phase_s, fetch_s, upload_s, errs = [], [], [], [], []
 
         def run_dataset(n_steps):
-            q = queue.Queue(maxsize=1)
+            q, dq, done = queue.Queue(maxsize=1), queue.Queue(maxsize=1), queue.Queue()
+
+            go = threading.Semaphore(1)   # the packer (pure Python + numpy: it holds the GIL) works while the compute
+                                          # thread sits in the solve call (GIL released), not beside its launch chain
 
             def packer():
                 for j in range(n_steps):
+                    go.acquire()
                     t0 = time.perf_counter()
-                    ar = arenas[j % 3]        # in flight at most: one consumed, one queued, one being packed
+                    ar = arenas[j % 4]        # in flight at most: one being read back, one consumed, one queued, one being packed
                     ar.reset()
                     pc = PackedConditions(ds_meshes, ds_samples, alloc=ar.empty)
                     pack_s.append(time.perf_counter() - t0)
+                    t0 = time.perf_counter()
+                    ar.upload(up_ctx)         # H2D of the big arrays on the packer's own context, under the running solve
+                    pc.use_device_copy(ar)
+                    upload_s.append(time.perf_counter() - t0)
                     q.put(pc)
 
-            th = threading.Thread(target=packer)
-            th.start()
+            def reader():
+                for j in range(n_steps):
+                    b = dq.get()
+                    t0 = time.perf_counter()
+                    try:
+                        _, _, ds_cls[0] = b.fetch_outputs(copy_ctx, out=ds_outs[j % 2], regions=ds_regs[j % 2])
+                    except Exception as e:    # keep draining so that the compute thread never blocks on a dead reader
+                        errs.append(e)
+                    fetch_s.append(time.perf_counter() - t0)
+                    done.put(b)           # destroyed by the compute thread (its context frees the device memory)
+
+            ths = [threading.Thread(target=packer), threading.Thread(target=reader)]
+            for th in ths:
+                th.start()
             for j in range(n_steps):
                 t0 = time.perf_counter()
                 pc = q.get()
                 t1_ = time.perf_counter()
-                with ctx.create_batch_from_conditions(pc) as b:
-                    t2_ = time.perf_counter()
-                    b.assemble().solve(a.rtol, a.max_iter).rasterize(ds_size, ds_affine, t1)
-                    t3_ = time.perf_counter()
-                    b.download(images=True, out=ds_outs[0])
-                    t4_ = time.perf_counter()
-                    b.rasterize_regions(ds_mask, out=ds_regs[0])
-                    ds_cls[0] = b.classify()
-                    t5_ = time.perf_counter()
-                phase_s.append((t1_ - t0, t2_ - t1_, t3_ - t2_, t4_ - t3_, t5_ - t4_, time.perf_counter() - t5_))
-            th.join()
+                while not done.empty():
+                    done.get().destroy()
+                b = ctx.create_batch_from_conditions(pc)
+                t2_ = time.perf_counter()
+                b.assemble()
+                go.release()
+                b.solve(a.rtol, a.max_iter).rasterize(ds_size, ds_affine, t1).stage_outputs(ds_mask)
+                t3_ = time.perf_counter()
+                dq.put(b)
+                phase_s.append((t1_ - t0, t2_ - t1_, t3_ - t2_, time.perf_counter() - t3_))
+            for th in ths:
+                th.join()
+            while not done.empty():
+                done.get().destroy()
+            if errs:
+                raise errs[0]
+            return (n_steps - 1) % 2
 
         pipe.synchronize()
         run_dataset(max(a.warmup, 2))
         ctx.synchronize()
         pack_s.clear()
         phase_s.clear()
+        fetch_s.clear()
+        upload_s.clear()
         barrier()
         ctx.event_record(4)
         t0 = time.perf_counter()
-        run_dataset(a.steps)
+        n_ds = max(a.steps, 12)      # the pipeline's fill (packing step 0) and drain (last read-back) are inside the timed region
+        last = run_dataset(n_ds)
         ctx.event_record(5)
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
         ms_ds = max_over_ranks(max(ctx.event_elapsed_ms(4, 5), wall_ms))
-        o = ds_outs[0]
+        copy_ctx.synchronize()
+        o = ds_outs[last]
         fl, em = ds_cls[0]
         same = (ds_items is items and np.array_equal(o.status, res0.status) and np.array_equal(o.u, res0.u))
-        dataset = {"value": total_of(n, world) * a.steps / (ms_ds * 1e-3), "unit": "samples/s", "ms_per_step": ms_ds / a.steps,
+        dataset = {"value": total_of(n, world) * n_ds / (ms_ds * 1e-3), "unit": "samples/s", "ms_per_step": ms_ds / n_ds, "steps": n_ds,
                    "h2d_bytes_per_step": int(probe.h2d_bytes + ds_affine.nbytes + ds_mask.nbytes),
                    "d2h_bytes_per_step": int(o.u.nbytes + o.ranges.nbytes + o.iters.nbytes + o.relres.nbytes + o.status.nbytes
                                              + o.images.nbytes + ds_regs[0].nbytes + 8 * n),
                    "host_pack_ms_per_step": 1e3 * float(np.mean(pack_s)) if pack_s else None,
-                   "gpu_thread_ms_per_step": dict(zip(("wait_for_packer", "create_from_conditions", "assemble_solve_raster",
-                                                       "download", "region_images_and_classifier", "destroy"),
-                                                       (1e3 * np.mean(phase_s, axis=0)).round(2).tolist())) if phase_s else None,
-                   "host_threads": "1 packer + 1 GPU thread, one context", "timer": "max(wall clock, CUDA events) around %d steps, max over ranks" % a.steps,
+                   "compute_thread_ms_per_step": dict(zip(("wait_for_packer", "create_from_conditions",
+                                                           "assemble_solve_raster_stage_regions_classifier", "hand_over"),
+                                                          (1e3 * np.mean(phase_s, axis=0)).round(2).tolist())) if phase_s else None,
+                   "reader_thread_fetch_ms_per_step": round(1e3 * float(np.mean(fetch_s)), 2) if fetch_s else None,
+                   "packer_thread_upload_ms_per_step": round(1e3 * float(np.mean(upload_s)), 2) if upload_s else None,
+                   "host_threads": "packer thread (packs step j + 1 and uploads its big arrays on a context of its own) + compute "
+                                   "thread (main context) + reader thread (copy context: D2H of step j - 1), all under the solve of step j",
+                   "timer": "max(wall clock until the last read-back has returned, CUDA events) around %d steps, max over ranks" % n_ds,
                    "region_images_per_step": n_img, "pinned_arena_spills": int(sum(x.spilled for x in arenas)),
                    "classifier": {"well_posed": int(((fl == 0) & (em == 0)).sum()), "floating": int((fl > 0).sum()),
                                   "empty_rows": int((em > 0).sum())},

@@ -17,10 +17,11 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfea_b200.so")
 # every symbol include/fea_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "fea_version", "fea_ctx_create", "fea_ctx_create_prio", "fea_ctx_destroy", "fea_last_error", "fea_host_alloc",
-    "fea_host_free", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
+    "fea_host_free", "fea_device_alloc", "fea_device_free", "fea_device_upload", "fea_ctx_synchronize", "fea_ctx_event_record", "fea_ctx_event_elapsed_ms",
     "fea_ctx_wait_ctx", "fea_ctx_set_int", "fea_ctx_kernel_launches", "fea_batch_create",
     "fea_batch_create_from_conditions", "fea_batch_get_setup", "fea_batch_get_materials", "fea_batch_rasterize_regions",
-    "fea_batch_classify", "fea_batch_rasterize_cell_components", "fea_batch_assemble",
+    "fea_batch_classify", "fea_batch_stage_outputs", "fea_batch_staged_region_images", "fea_batch_fetch_outputs",
+    "fea_batch_rasterize_cell_components", "fea_batch_assemble",
     "fea_batch_solve", "fea_batch_rasterize", "fea_batch_destroy", "fea_batch_download",
     "fea_batch_download_images", "fea_batch_rasterize_flags", "fea_batch_cell_strain_stress", "fea_batch_get_info", "fea_batch_get_solve_stats", "fea_batch_get_refine_rounds",
     "fea_batch_get_timed_launches",
@@ -114,6 +115,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
         "fea_host_free": (C.c_int, [P, P]),
         "fea_ctx_synchronize": (C.c_int, [P]),
+        "fea_device_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
+        "fea_device_free": (C.c_int, [P, P]),
+        "fea_device_upload": (C.c_int, [P, P, P, C.c_size_t]),
         "fea_ctx_event_record": (C.c_int, [P, I32]),
         "fea_ctx_event_elapsed_ms": (C.c_int, [P, I32, I32, P]),
         "fea_ctx_kernel_launches": (C.c_int, [P, P]),
@@ -123,6 +127,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "fea_batch_get_materials": (C.c_int, [P, P, P, P]),
         "fea_batch_rasterize_regions": (C.c_int, [P, P, P]),
         "fea_batch_classify": (C.c_int, [P, P, P]),
+        "fea_batch_stage_outputs": (C.c_int, [P, P]),
+        "fea_batch_staged_region_images": (C.c_int, [P, P]),
+        "fea_batch_fetch_outputs": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P]),
         "fea_batch_rasterize_cell_components": (C.c_int, [P, I32, I32, P, F64, P, P]),
         "fea_batch_assemble": (C.c_int, [P]),
         "fea_batch_solve": (C.c_int, [P, F64, I32]),

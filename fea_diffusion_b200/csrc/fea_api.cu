@@ -58,6 +58,7 @@ void api_free_batch(fea_batch* hb) {
   cudaSetDevice(b.ctx->device);
   for (void* p : b.allocs) cudaFreeAsync(p, b.ctx->stream);
   b.allocs.clear();
+  if (b.ev_staged) cudaEventDestroy(b.ev_staged);
   delete hb;
 }
 
@@ -251,6 +252,29 @@ int fea_host_free(fea_ctx* ctx, void* p) {
   if (p) CK(ctx, cudaFreeHost(p));
   return FEA_OK;
 }
+// Device staging buffers: a producer thread with its own context uploads the big input arrays of the NEXT batch
+// (coordinates, connectivity, material coordinate lists) while the solving context is busy; the batch is then
+// created from device pointers (fea_conditions_desc.xy / conn / mat_coords) with device-to-device copies.
+int fea_device_alloc(fea_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return FEA_BAD_ARG;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return FEA_OK;
+}
+int fea_device_free(fea_ctx* ctx, void* p) {
+  if (!ctx) return FEA_BAD_ARG;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaFree(p));
+  return FEA_OK;
+}
+int fea_device_upload(fea_ctx* ctx, void* dev, const void* host, size_t bytes) {
+  if (!ctx || (bytes && (!dev || !host))) return FEA_BAD_ARG;
+  CK(ctx, cudaSetDevice(ctx->c.device));
+  CK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->c.stream));
+  CK(ctx, cudaStreamSynchronize(ctx->c.stream));
+  return FEA_OK;
+}
+
 int fea_ctx_synchronize(fea_ctx* ctx) {
   if (!ctx) return FEA_BAD_ARG;
   CK(ctx, cudaStreamSynchronize(ctx->c.stream));

@@ -151,6 +151,11 @@ struct Batch {
   int32_t* rcount = nullptr;       // [NR] vertices per region
   int8_t* creg_local = nullptr;    // [NC] sample-local material-table index of each cell, -1 = none
   int32_t* n_reg_used = nullptr;   // [ns] material-table entries in use (terms + overlap combinations)
+  // ---- outputs staged on the device for a reader on another stream (fea_batch_stage_outputs) ----
+  std::vector<int64_t> stage_field_off;   // [ns+1] first region image of each sample
+  uint8_t* stage_regions = nullptr;       // [stage_field_off[ns]][size][size]
+  int32_t* stage_class = nullptr;         // [2*ns] floating parts, empty vertices
+  cudaEvent_t ev_staged = nullptr;        // recorded behind the last kernel that writes an output
 };
 
 }  // namespace fea

@@ -648,8 +648,8 @@ int fea_batch_create_from_conditions(fea_ctx* ctx, const fea_conditions_desc* d,
   int32_t* d_err = nullptr;
   A(dalloc(b, &d_err, 1));
   A(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
-  A(cudaMemcpyAsync(m_xy, d->xy, sizeof(double) * 2 * MV, cudaMemcpyHostToDevice, st));
-  A(cudaMemcpyAsync(m_conn, d->conn, sizeof(int32_t) * MC * npc, cudaMemcpyHostToDevice, st));
+  A(cudaMemcpyAsync(m_xy, d->xy, sizeof(double) * 2 * MV, cudaMemcpyDefault, st));       // host or device (fea_device_upload)
+  A(cudaMemcpyAsync(m_conn, d->conn, sizeof(int32_t) * MC * npc, cudaMemcpyDefault, st));
   A(cudaMemcpyAsync(m_vtx_off, d->mesh_vtx_off, sizeof(int64_t) * (nm + 1), cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(m_cell_off, d->mesh_cell_off, sizeof(int64_t) * (nm + 1), cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(d_voff, vtx_off.data(), sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
@@ -661,7 +661,7 @@ int fea_batch_create_from_conditions(fea_ctx* ctx, const fea_conditions_desc* d,
   A(cudaMemcpyAsync(d_regoff, reg_off.data(), sizeof(int32_t) * (ns + 1), cudaMemcpyHostToDevice, st));
   A(cudaMemcpyAsync(d_coord_off, d->mat_coord_off, sizeof(int64_t) * (n_matreg + 1), cudaMemcpyHostToDevice, st));
   if (n_matreg) A(cudaMemcpyAsync(d_E_nu, d->mat_E_nu, sizeof(double) * 2 * n_matreg, cudaMemcpyHostToDevice, st));
-  if (n_scalars) A(cudaMemcpyAsync(d_coords, d->mat_coords, sizeof(double) * n_scalars, cudaMemcpyHostToDevice, st));
+  if (n_scalars) A(cudaMemcpyAsync(d_coords, d->mat_coords, sizeof(double) * n_scalars, cudaMemcpyDefault, st));
   A(cudaMemsetAsync(tab, 0xFF, sizeof(unsigned long long) * std::max<int64_t>(tab_slots, 1), st));
   A(cudaMemsetAsync(cell_member, 0, sizeof(uint32_t) * std::max<int64_t>(b.NC, 1), st));
   A(cudaMemsetAsync(combo_mask, 0, sizeof(uint32_t) * ns * kMaxCombo, st));
@@ -806,6 +806,73 @@ int fea_batch_classify(fea_batch* hb, int32_t* floating_parts, int32_t* empty_ve
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFreeAsync(dv, st);
   if (e != cudaSuccess) return api_fail(ctx, FEA_CUDA_ERROR, "fea_batch_classify", e);
+  return FEA_OK;
+}
+
+// ---- staged outputs: everything a dataset writer reads, produced on the batch's stream and read back on
+// another one.  The D2H copies of batch j (u, images, region images: ~60 MB for 400 plate-conditions) then run
+// on a copy engine while the batch's own context already solves batch j + 1.
+int fea_batch_stage_outputs(fea_batch* hb, const uint8_t* with_plate_mask) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = hb->owner;
+  Batch& b = hb->b;
+  if (!b.rasterized) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_stage_outputs before fea_batch_rasterize");
+  CKC(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  if (!b.ev_staged) CKC(ctx, cudaEventCreateWithFlags(&b.ev_staged, cudaEventDisableTiming));
+  if (b.from_conditions && !b.stage_class) {
+    b.stage_field_off.assign(b.ns + 1, 0);
+    for (int s = 0; s < b.ns; ++s)
+      b.stage_field_off[s + 1] = b.stage_field_off[s] + (b.sreg_off[s + 1] - b.sreg_off[s] - 1) + ((with_plate_mask && with_plate_mask[s]) ? 1 : 0);
+    const int64_t n_img = b.stage_field_off[b.ns];
+    const size_t per = (size_t)b.img_size * b.img_size;
+    CKC(ctx, dalloc(b, &b.stage_class, (int64_t)2 * b.ns));
+    CKC(ctx, launch_classify(b, b.stage_class, b.stage_class + b.ns));
+    if (n_img > 0) {
+      int64_t* tab = nullptr;
+      CKC(ctx, dalloc(b, &tab, (int64_t)2 * (b.ns + 1)));
+      CKC(ctx, dalloc(b, &b.stage_regions, (int64_t)(n_img * per)));
+      CKC(ctx, cudaMemcpyAsync(tab, b.stage_field_off.data(), sizeof(int64_t) * (b.ns + 1), cudaMemcpyHostToDevice, st));
+      CKC(ctx, cudaMemcpyAsync(tab + b.ns + 1, b.flag_off.data(), sizeof(int64_t) * (b.ns + 1), cudaMemcpyHostToDevice, st));
+      CKC(ctx, launch_raster_flags(b, n_img, tab, tab + b.ns + 1, b.rflags, b.stage_regions));
+      ctx->c.launches += 1;
+    }
+  }
+  CKC(ctx, cudaEventRecord(b.ev_staged, st));
+  return FEA_OK;
+}
+
+int fea_batch_staged_region_images(fea_batch* hb, int64_t* n_images) {
+  if (!hb || !n_images) return FEA_BAD_ARG;
+  *n_images = hb->b.stage_field_off.empty() ? 0 : hb->b.stage_field_off[hb->b.ns];
+  return FEA_OK;
+}
+
+int fea_batch_fetch_outputs(fea_batch* hb, fea_ctx* copy_ctx, double* u, double* ranges, int32_t* iters, double* relres,
+                            int32_t* status, uint8_t* images, uint8_t* region_images, int32_t* floating_parts,
+                            int32_t* empty_vertices) {
+  if (!hb) return FEA_BAD_ARG;
+  fea_ctx* ctx = copy_ctx ? copy_ctx : hb->owner;     // errors are reported on the calling thread's context
+  const Batch& b = hb->b;
+  if (!b.ev_staged) return api_fail(ctx, FEA_BAD_STATE, "fea_batch_fetch_outputs before fea_batch_stage_outputs");
+  if ((region_images || floating_parts || empty_vertices) && !b.stage_class)
+    return api_fail(ctx, FEA_BAD_STATE, "region images / classifier need a batch made by fea_batch_create_from_conditions");
+  if (ctx->c.device != hb->owner->c.device) return api_fail(ctx, FEA_BAD_ARG, "copy context on another device");
+  CKC(ctx, cudaSetDevice(ctx->c.device));
+  cudaStream_t st = ctx->c.stream;
+  CKC(ctx, cudaStreamWaitEvent(st, b.ev_staged, 0));
+  const size_t per = (size_t)b.img_size * b.img_size;
+  if (u) CKC(ctx, cudaMemcpyAsync(u, b.u, sizeof(double) * 2 * b.NV, cudaMemcpyDeviceToHost, st));
+  if (ranges) CKC(ctx, cudaMemcpyAsync(ranges, b.ranges, sizeof(double) * 4 * b.ns, cudaMemcpyDeviceToHost, st));
+  if (iters) CKC(ctx, cudaMemcpyAsync(iters, b.sc.iters, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (relres) CKC(ctx, cudaMemcpyAsync(relres, b.relres, sizeof(double) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (status) CKC(ctx, cudaMemcpyAsync(status, b.sc.status, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (images) CKC(ctx, cudaMemcpyAsync(images, b.images, (size_t)b.ns * 2 * per, cudaMemcpyDeviceToHost, st));
+  if (region_images && b.stage_regions)
+    CKC(ctx, cudaMemcpyAsync(region_images, b.stage_regions, (size_t)b.stage_field_off[b.ns] * per, cudaMemcpyDeviceToHost, st));
+  if (floating_parts) CKC(ctx, cudaMemcpyAsync(floating_parts, b.stage_class, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  if (empty_vertices) CKC(ctx, cudaMemcpyAsync(empty_vertices, b.stage_class + b.ns, sizeof(int32_t) * b.ns, cudaMemcpyDeviceToHost, st));
+  CKC(ctx, cudaStreamSynchronize(st));
   return FEA_OK;
 }
 

@@ -184,8 +184,11 @@ cudaError_t launch_raster_fields(cudaStream_t st, int npc, int64_t n_v, int64_t 
 // Region-flag images of every sample of a batch (regions_<Region>.png of the dataset tree,
 // reference fea_analysis.py:508-524): 0/1 vertex flags interpolated over the owner triangle of each
 // pixel (owner map of the preceding fea_batch_rasterize), clim (0, 1), same colour map.
+// One thread per (sample, pixel): the owner triangle and its barycentric weights are found once and reused for
+// every region image of the sample (a dozen or more); a triangle none of whose vertices is in the region -- almost
+// all of them, regions are small -- is white without any arithmetic.
 template <int NPC>
-__global__ void k_raster_flags(int ns, int size, int64_t n_img, const int64_t* __restrict__ field_off,
+__global__ void k_raster_flags(int ns, int size, const int64_t* __restrict__ field_off,
                                const int64_t* __restrict__ flag_off, const int64_t* __restrict__ cell_off,
                                const int64_t* __restrict__ vtx_off, const int32_t* __restrict__ conn,
                                const double* __restrict__ xy, const double* __restrict__ affine,
@@ -194,41 +197,50 @@ __global__ void k_raster_flags(int ns, int size, int64_t n_img, const int64_t* _
   constexpr int SUB = (NPC == 3) ? 1 : 2;
   const int64_t per = (int64_t)size * size;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_img * per) return;
-  const int64_t img = gid / per, lp = gid - img * per;
-  const int s = seg_of(field_off, ns, img);
-  const int f = (int)(img - field_off[s]);
-  const int j = (int)(lp / size), i = (int)(lp - (int64_t)j * size);
-  const int32_t o = owner[(int64_t)s * per + lp];
-  uint8_t g = 255;
-  if (o != 0x7fffffff) {
-    const int64_t cell = cell_off[s] + o / SUB;
-    Tri t;
-    int32_t vid[3];
-    load_tri<NPC>(cell, o % SUB, conn, xy, affine + 4 * s, t, vid);
-    double w[3], a2;
-    bary(t, (double)i + 0.5, (double)j + 0.5, w, &a2);
-    const int64_t nv = vtx_off[s + 1] - vtx_off[s];
-    const uint8_t* fl = flags + flag_off[s] + (int64_t)f * nv - vtx_off[s];   // indexed by GLOBAL vertex id
-    const double v0 = fl[vid[0]] ? 1.0 : 0.0, v1 = fl[vid[1]] ? 1.0 : 0.0, v2 = fl[vid[2]] ? 1.0 : 0.0;
-    double tt = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(w[0], v0), __dmul_rn(w[1], v1)), __dmul_rn(w[2], v2)), a2);
-    tt = fmin(fmax(tt, 0.0), 1.0);
-    g = (uint8_t)(255.0 - fmin(floor(__dmul_rn(256.0, tt)), 255.0));
+  if (gid >= (int64_t)ns * per) return;
+  const int s = (int)(gid / per);
+  const int64_t lp = gid - (int64_t)s * per;
+  const int nf = (int)(field_off[s + 1] - field_off[s]);
+  if (nf == 0) return;
+  uint8_t* __restrict__ out = images + field_off[s] * per + lp;
+  const int32_t o = owner[gid];
+  if (o == 0x7fffffff) {
+    for (int f = 0; f < nf; ++f) out[(int64_t)f * per] = 255;
+    return;
   }
-  images[gid] = g;
+  const int j = (int)(lp / size), i = (int)(lp - (int64_t)j * size);
+  const int64_t cell = cell_off[s] + o / SUB;
+  Tri t;
+  int32_t vid[3];
+  load_tri<NPC>(cell, o % SUB, conn, xy, affine + 4 * s, t, vid);
+  double w[3], a2;
+  bary(t, (double)i + 0.5, (double)j + 0.5, w, &a2);
+  const int64_t nv = vtx_off[s + 1] - vtx_off[s];
+  const uint8_t* fl = flags + flag_off[s] - vtx_off[s];   // indexed by GLOBAL vertex id
+  for (int f = 0; f < nf; ++f, fl += nv) {
+    const uint8_t f0 = fl[vid[0]], f1 = fl[vid[1]], f2 = fl[vid[2]];
+    uint8_t g = 255;
+    if (f0 | f1 | f2) {
+      const double v0 = f0 ? 1.0 : 0.0, v1 = f1 ? 1.0 : 0.0, v2 = f2 ? 1.0 : 0.0;
+      double tt = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(w[0], v0), __dmul_rn(w[1], v1)), __dmul_rn(w[2], v2)), a2);
+      tt = fmin(fmax(tt, 0.0), 1.0);
+      g = (uint8_t)(255.0 - fmin(floor(__dmul_rn(256.0, tt)), 255.0));
+    }
+    out[(int64_t)f * per] = g;
+  }
 }
 
 cudaError_t launch_raster_flags(Batch& b, int64_t n_img, const int64_t* d_field_off, const int64_t* d_flag_off,
                                 const uint8_t* d_flags, uint8_t* d_images) {
   const int T = 256;
-  const int64_t n = n_img * b.img_size * b.img_size;
-  if (n == 0) return cudaSuccess;
+  const int64_t n = (int64_t)b.ns * b.img_size * b.img_size;
+  if (n == 0 || n_img == 0) return cudaSuccess;
   const unsigned g = (unsigned)((n + T - 1) / T);
   if (b.npc == 3)
-    k_raster_flags<3><<<g, T, 0, b.ctx->stream>>>(b.ns, b.img_size, n_img, d_field_off, d_flag_off, b.d_cell_off, b.d_vtx_off,
+    k_raster_flags<3><<<g, T, 0, b.ctx->stream>>>(b.ns, b.img_size, d_field_off, d_flag_off, b.d_cell_off, b.d_vtx_off,
                                                   b.conn, b.xy, b.affine, b.owner, d_flags, d_images);
   else
-    k_raster_flags<4><<<g, T, 0, b.ctx->stream>>>(b.ns, b.img_size, n_img, d_field_off, d_flag_off, b.d_cell_off, b.d_vtx_off,
+    k_raster_flags<4><<<g, T, 0, b.ctx->stream>>>(b.ns, b.img_size, d_field_off, d_flag_off, b.d_cell_off, b.d_vtx_off,
                                                   b.conn, b.xy, b.affine, b.owner, d_flags, d_images);
   return cudaGetLastError();
 }

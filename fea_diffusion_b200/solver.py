@@ -211,6 +211,16 @@ class PackedConditions:
     def split_vertices(self, a: np.ndarray) -> List[np.ndarray]:
         return [a[self.vtx_off[s]:self.vtx_off[s + 1]] for s in range(self.n)]
 
+    def use_device_copy(self, arena: "PinnedArena"):
+        """Point the descriptor's big arrays (xy, conn, mat_coords) at the device copy of ``arena``
+        (``PinnedArena.upload``): the batch is then created with device-to-device copies."""
+        for f in ("xy", "conn", "mat_coords"):
+            a = getattr(self, f)
+            d = arena.device_address(a)
+            if d is not None:
+                setattr(self.desc, f, d)
+        return self
+
     def sample_conn(self, s: int) -> np.ndarray:
         m = int(self.sample_mesh[s])
         return self.conn[self.mesh_cell_off[m]:self.mesh_cell_off[m + 1]]
@@ -269,6 +279,27 @@ class PinnedArena:
         self.off = o + n
         return self.buf[o:o + n].view(dtype).reshape(shape)
 
+    def upload(self, ctx: "Context"):
+        """Copy what has been handed out so far into a device buffer of the same size on ``ctx``'s stream
+        (fea_device_upload; returns when the copy is done).  ``ctx`` is the calling thread's own context."""
+        if getattr(self, "dev", None) is None:
+            self.dev = ctx.device_alloc(self.buf.size)
+            self._dev_ctx = ctx
+        ctx.device_upload(self.dev, self.buf, self.off)
+        return self
+
+    def device_address(self, a: np.ndarray):
+        """Device address of an array carved from this arena (None if it lives elsewhere or nothing was uploaded)."""
+        if getattr(self, "dev", None) is None or a.size == 0:
+            return None
+        o = a.ctypes.data - self.buf.ctypes.data
+        return self.dev + o if 0 <= o and o + a.nbytes <= self.off else None
+
+    def release_device(self):
+        if getattr(self, "dev", None) is not None:
+            self._dev_ctx.device_free(self.dev)
+            self.dev = None
+
 
 class Context:
     """One fea_ctx: a GPU and a stream.  Not thread-safe; use one per host thread."""
@@ -325,6 +356,19 @@ class Context:
         n = C.c_int64()
         self._check(self.lib.fea_ctx_kernel_launches(self.h, C.byref(n)))
         return int(n.value)
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.fea_device_alloc(self.h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, dev: int):
+        self._check(self.lib.fea_device_free(self.h, C.c_void_p(dev)))
+
+    def device_upload(self, dev: int, host: np.ndarray, nbytes: Optional[int] = None):
+        """H2D of the first ``nbytes`` of ``host`` into a ``device_alloc`` buffer; synchronised on return."""
+        n = host.nbytes if nbytes is None else int(nbytes)
+        self._check(self.lib.fea_device_upload(self.h, C.c_void_p(dev), ptr(host), n))
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         """numpy array over page-locked host memory (fea_host_alloc); released by close() -- the array
@@ -499,6 +543,43 @@ class Batch:
         a, z = np.empty(n, np.int32), np.empty(n, np.int32)
         self.ctx._check(self.ctx.lib.fea_batch_classify(self.h, ptr(a), ptr(z)))
         return a, z
+
+    def stage_outputs(self, with_plate_mask: Optional[Sequence[bool]] = None):
+        """Enqueue the region images (+ plate masks) and the classifier into device buffers and mark the batch
+        ready for ``fetch_outputs`` -- no synchronisation (fea_batch_stage_outputs)."""
+        m = None if with_plate_mask is None else np.ascontiguousarray(with_plate_mask, dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.fea_batch_stage_outputs(self.h, ptr(m)))
+        self._stage_mask = m
+        return self
+
+    def fetch_outputs(self, copy_ctx: Optional["Context"] = None, out: Optional[BatchResult] = None,
+                      regions: Optional[np.ndarray] = None, classifier: bool = True):
+        """Read a staged batch back on ``copy_ctx``'s stream (another host thread may call this while the
+        batch's own context runs the next batch): (BatchResult with images, region images per sample or None,
+        (floating_parts, empty_vertices) or None)."""
+        p = self.packed
+        c = copy_ctx or self.ctx
+        n, size = p.n, self.image_size
+        if out is None:
+            out = BatchResult(u=np.empty((p.n_vertices, 2)), ranges=np.empty((n, 4)), iters=np.empty(n, np.int32),
+                              relres=np.empty(n), status=np.empty(n, np.int32), images=np.empty((n, 2, size, size), np.uint8))
+        n_img = C.c_int64()
+        c._check(c.lib.fea_batch_staged_region_images(self.h, C.byref(n_img)))
+        reg = None
+        if n_img.value:
+            shape = (n_img.value, size, size)
+            reg = np.empty(shape, np.uint8) if regions is None or regions.size < int(np.prod(shape)) else \
+                regions.reshape(-1)[:int(np.prod(shape))].reshape(shape)
+        cls = (np.empty(n, np.int32), np.empty(n, np.int32)) if classifier and hasattr(p, "n_regions") else None
+        c._check(c.lib.fea_batch_fetch_outputs(self.h, c.h if copy_ctx is not None else None, ptr(out.u), ptr(out.ranges),
+                                               ptr(out.iters), ptr(out.relres), ptr(out.status), ptr(out.images), ptr(reg),
+                                               ptr(cls[0]) if cls else None, ptr(cls[1]) if cls else None))
+        per = None
+        if reg is not None:
+            m = self._stage_mask if getattr(self, "_stage_mask", None) is not None else np.zeros(n, np.uint8)
+            off = np.concatenate([[0], np.cumsum(p.n_regions + m)]).astype(np.int64)
+            per = [reg[off[s]:off[s + 1]] for s in range(n)]
+        return out, per, cls
 
     CELL_FIELDS = {"stress_x": 0, "stress_y": 1, "strain_x": 2, "strain_y": 3}
 

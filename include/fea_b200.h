@@ -185,6 +185,14 @@ const char* fea_last_error(const fea_ctx* ctx);
 int  fea_host_alloc(fea_ctx* ctx, size_t bytes, void** out);
 int  fea_host_free(fea_ctx* ctx, void* p);
 int  fea_ctx_synchronize(fea_ctx* ctx);
+/* Device staging for pipelined producers: fea_device_upload copies `bytes` from (pinned) host memory into a
+ * buffer of fea_device_alloc on the context's stream and returns when the copy is done.  A producer thread with
+ * a context of its own uploads the big arrays of the NEXT batch while the solving context is busy;
+ * fea_conditions_desc.xy / conn / mat_coords may then point into that device buffer (every other field of the
+ * descriptor stays in host memory). */
+int  fea_device_alloc(fea_ctx* ctx, size_t bytes, void** out);
+int  fea_device_free(fea_ctx* ctx, void* p);
+int  fea_device_upload(fea_ctx* ctx, void* dev, const void* host, size_t bytes);
 /* CUDA events on the context's stream, for timing regions that span several calls
  * (slot in [0, 8)); elapsed is valid once the later event has completed. */
 int  fea_ctx_event_record(fea_ctx* ctx, int32_t slot);
@@ -304,6 +312,22 @@ int  fea_batch_rasterize_regions(fea_batch* b, const uint8_t* with_plate_mask, u
  * of the stiffness mesh (cells connected through shared edges) with fewer than two fixed vertices,
  * empty_vertices[s] = active vertices touching no stiffness cell (the reference's SuperLU-NaN case). */
 int  fea_batch_classify(fea_batch* b, int32_t* floating_parts, int32_t* empty_vertices);
+/* Staged outputs: the read-back of one batch overlapped with the solve of the next (the batched form of the
+ * reference's per-condition file writes, generate.py:126-157, for a pipelined generator).
+ * fea_batch_stage_outputs (after fea_batch_rasterize, on the batch's own context) enqueues what is still
+ * missing -- for a batch made by fea_batch_create_from_conditions the region images (as
+ * fea_batch_rasterize_regions, with_plate_mask may be NULL) and the classifier -- into device buffers the batch
+ * owns, records an event behind them and returns without synchronising.
+ * fea_batch_fetch_outputs copies the results to host buffers (any may be NULL; pinned memory for real overlap)
+ * on the stream of `copy_ctx` (NULL: the batch's own context) after that event and synchronises only that
+ * stream; it may run on another host thread while the batch's context already works on the next batch.
+ * region_images [fea_batch_staged_region_images][size][size]; the batch is destroyed by its own context's
+ * thread after the fetch has returned. */
+int  fea_batch_stage_outputs(fea_batch* b, const uint8_t* with_plate_mask);
+int  fea_batch_staged_region_images(fea_batch* b, int64_t* n_images);
+int  fea_batch_fetch_outputs(fea_batch* b, fea_ctx* copy_ctx, double* u, double* ranges, int32_t* iters,
+                             double* relres, int32_t* status, uint8_t* images, uint8_t* region_images,
+                             int32_t* floating_parts, int32_t* empty_vertices);
 
 /* ---- inspection entry points used by the parity tests -------------------- */
 /* per-sample reduced sizes: n_active_dofs[s], nnz[s] (scalar CSR) */

@@ -177,6 +177,66 @@ def test_region_images_from_device_flags(ctx):
         assert a.shape == r.shape and np.array_equal(a, r)
 
 
+def test_staged_outputs_fetched_on_a_copy_context(ctx):
+    """fea_batch_stage_outputs / fea_batch_fetch_outputs: the read-back of batch j on a second context's stream, from
+    another host thread, while the first context already solves batch j + 1 -- same bytes as the synchronous calls."""
+    import threading
+    items, _ = build_workload(3, 2, 64, seed0=9)
+    meshes, samples, index = [], [], {}
+    for it in items:
+        if it.plate not in index:
+            index[it.plate] = len(meshes)
+            meshes.append((it.setup.coors, it.setup.conn))
+        samples.append((index[it.plate], it.kwargs))
+    pc = PackedConditions(meshes, samples)
+    size = max(it.size for it in items)
+    affine = np.stack([it.affine for it in items])
+    mask = [it.condition == 0 for it in items]
+    with ctx.create_batch_from_conditions(pc) as b:
+        b.assemble().solve(1e-10, 50000).rasterize(size, affine, 0.1)
+        want = b.download(images=True)
+        want_reg = [r.copy() for r in b.rasterize_regions(mask)]
+        want_cls = b.classify()
+    copy_ctx = Context(0)
+    got = {}
+    b1 = ctx.create_batch_from_conditions(pc)
+    b1.assemble().solve(1e-10, 50000).rasterize(size, affine, 0.1).stage_outputs(mask)
+    th = threading.Thread(target=lambda: got.update(r=b1.fetch_outputs(copy_ctx)))
+    th.start()
+    with ctx.create_batch_from_conditions(pc) as b2:       # the next batch on the first context meanwhile
+        b2.assemble().solve(1e-10, 50000).rasterize(size, affine, 0.1)
+        again = b2.download(images=True)
+    th.join()
+    b1.destroy()
+    # the big input arrays uploaded ahead of time on another context (fea_device_upload): the batch is created from
+    # device pointers and must come out the same
+    from fea_diffusion_b200.solver import PinnedArena
+    arena = PinnedArena(ctx, pc.h2d_bytes + (1 << 16))
+    pc_dev = PackedConditions(meshes, samples, alloc=arena.empty)
+    arena.upload(copy_ctx)
+    pc_dev.use_device_copy(arena)
+    assert pc_dev.desc.xy != pc_dev.xy.ctypes.data and arena.spilled == 0
+    with ctx.create_batch_from_conditions(pc_dev) as b4:
+        b4.assemble().solve(1e-10, 50000).rasterize(size, affine, 0.1)
+        r4 = b4.download(images=True)
+    arena.release_device()
+    copy_ctx.close()
+    assert np.array_equal(r4.u, want.u, equal_nan=True) and np.array_equal(r4.images, want.images)
+    res, reg, cls = got["r"]
+    for r in (res, again):
+        assert np.array_equal(r.u, want.u, equal_nan=True) and np.array_equal(r.status, want.status)
+        assert np.array_equal(r.ranges, want.ranges, equal_nan=True) and np.array_equal(r.iters, want.iters)
+        assert np.array_equal(r.images, want.images)
+    assert np.array_equal(res.relres, want.relres, equal_nan=True)
+    assert len(reg) == len(want_reg) and all(np.array_equal(a, w) for a, w in zip(reg, want_reg))
+    assert np.array_equal(cls[0], want_cls[0]) and np.array_equal(cls[1], want_cls[1])
+    # a batch made from arrays stages too (no region images, no classifier)
+    with ctx.create_batch(pack([it.setup.sample for it in items])) as b3:
+        b3.assemble().solve(1e-10, 50000).rasterize(size, affine, 0.1).stage_outputs()
+        r3, reg3, cls3 = b3.fetch_outputs()
+    assert reg3 is None and cls3 is None and np.array_equal(r3.u, want.u, equal_nan=True)
+
+
 def test_bad_tags_are_rejected(ctx):
     from fea_diffusion_b200 import FeaError
     co = np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]])
