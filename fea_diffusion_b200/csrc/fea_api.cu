@@ -199,10 +199,12 @@ int fea_ctx_create_prio(int device, int priority, fea_ctx** out) {
   cudaEventCreate(&ctx->c.ev_t0);
   cudaEventCreate(&ctx->c.ev_t1);
   cudaEventCreateWithFlags(&ctx->c.ev_fork, cudaEventDisableTiming);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < Ctx::kAux; ++i) {   // (the device has fewer priority levels than classes: the smallest classes share the most urgent one)
     cudaStreamCreateWithPriority(&ctx->c.aux[i], cudaStreamNonBlocking, std::max(hi, priority - 1 - i));
     cudaEventCreateWithFlags(&ctx->c.ev_join[i], cudaEventDisableTiming);
   }
+  ctx->c.prio_lo = priority;
+  ctx->c.prio_hi = hi;
   cudaEventCreate(&ctx->c.ev_c0);
   cudaEventCreate(&ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventCreate(&ev);
@@ -224,10 +226,12 @@ int fea_ctx_destroy(fea_ctx* ctx) {
   cudaEventDestroy(ctx->c.ev_t0);
   cudaEventDestroy(ctx->c.ev_t1);
   cudaEventDestroy(ctx->c.ev_fork);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < Ctx::kAux; ++i) {
     cudaEventDestroy(ctx->c.ev_join[i]);
     if (ctx->c.aux[i]) cudaStreamDestroy(ctx->c.aux[i]);
   }
+  for (auto& st : ctx->c.prio_streams)
+    if (st) cudaStreamDestroy(st);
   cudaEventDestroy(ctx->c.ev_c0);
   cudaEventDestroy(ctx->c.ev_c1);
   for (auto& ev : ctx->ev_user) cudaEventDestroy(ev);
@@ -308,6 +312,7 @@ int fea_ctx_set_int(fea_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "pcg_path") == 0) ctx->c.pcg_path = value == 1 ? 1 : 0;
   else if (strcmp(key, "row_order") == 0) ctx->c.row_order = (value >= 1 && value <= 3) ? (int)value : 0;
   else if (strcmp(key, "cluster_halo_cap") == 0) ctx->c.cluster_halo_cap = value < 0 ? 0 : value > (1 << 30) ? (1 << 30) : (int)value;
+  else if (strcmp(key, "cluster_prio") == 0) ctx->c.cluster_prio = (int)value;
   else if (strcmp(key, "cluster_min") == 0) ctx->c.cluster_min = value < 1 ? 1 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "refine_rounds") == 0) ctx->c.refine_rounds = value < 0 ? 0 : value > 8 ? 8 : (int)value;
   else if (strcmp(key, "spmv_variant") == 0) ctx->c.spmv_variant = (int)value;

@@ -41,8 +41,13 @@ struct Ctx {
   int row_order = 3;                   // solver row order: 0 = input numbering, 1 = Morton, 2 = strips, 3 = auto
   int cluster_min = 1;                 // smallest cluster size used (1..8)
   int cluster_halo_cap = 1 << 30;      // test knob: on-chip systems with a larger per-CTA halo go to the streaming path
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // cluster kernels of different classes run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  static constexpr int kAux = 8;       // one stream per cluster class (1..8) beside the main stream
+  cudaStream_t aux[kAux] = {};         // cluster kernels of different classes run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
+  int prio_lo = 0, prio_hi = 0;        // least / most urgent stream priority this context may use
+  cudaStream_t prio_streams[9] = {};   // (cluster_prio knob) stream of class k at its chosen urgency, made on demand
+  int prio_streams_key = 0;
+  int cluster_prio = 0;                // tuning knob: decimal digit k (from the right) = urgency 1..6 of class k, 0 = default rule
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
   int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };

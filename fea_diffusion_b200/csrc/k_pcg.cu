@@ -541,14 +541,34 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
     // main stream and three auxiliary streams so that their clusters are co-scheduled and small
     // clusters fill the SMs that larger ones cannot use (GPC granularity)
     cudaEventRecord(c.ev_fork, st);
-    bool used[3] = {false, false, false};
+    bool used[Ctx::kAux] = {};
+    cudaStream_t aux_of[Ctx::kAux];
+    for (int a = 0; a < Ctx::kAux; ++a) aux_of[a] = c.aux[a];
+    if (c.cluster_prio != c.prio_streams_key) {   // tuning knob changed: streams at the requested urgencies
+      for (auto& s2 : c.prio_streams) { if (s2) cudaStreamDestroy(s2); s2 = nullptr; }
+      c.prio_streams_key = c.cluster_prio;
+    }
     int slot = 0;
     for (int k = 8; k >= 1; --k) {
       if (!P.cl_cnt[k]) continue;
       cudaStream_t ks = st;
-      if (slot > 0 && c.aux[(slot - 1) % 3]) {
-        const int a = (slot - 1) % 3;
-        ks = c.aux[a];
+      int a = -1;
+      if (c.cluster_prio) {
+        int digit = c.cluster_prio;
+        for (int i = 1; i < k; ++i) digit /= 10;
+        digit %= 10;
+        if (digit > 0) {
+          if (!c.prio_streams[k]) {
+            const int pr = c.prio_lo - (digit - 1) < c.prio_hi ? c.prio_hi : c.prio_lo - (digit - 1);
+            cudaStreamCreateWithPriority(&c.prio_streams[k], cudaStreamNonBlocking, pr);
+          }
+          a = k - 1;                                 // join-event slot of this class
+          aux_of[a] = c.prio_streams[k];
+        }
+      }
+      if (a < 0 && slot > 0 && c.aux[slot - 1]) a = slot - 1;
+      if (a >= 0) {
+        ks = aux_of[a];
         if (!used[a]) cudaStreamWaitEvent(ks, c.ev_fork, 0);
         used[a] = true;
       }
@@ -556,9 +576,9 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       launches += 1;
       ++slot;
     }
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < Ctx::kAux; ++a) {
       if (!used[a]) continue;
-      cudaEventRecord(c.ev_join[a], c.aux[a]);
+      cudaEventRecord(c.ev_join[a], aux_of[a]);
       cudaStreamWaitEvent(st, c.ev_join[a], 0);
     }
     cudaEventRecord(c.ev_c1, st);

@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "fea_internal.cuh"
 #include "pcg_params.cuh"
@@ -44,6 +45,16 @@ namespace fea {
 
 #if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 __device__ unsigned long long g_cl_prof[16];
+#endif
+#ifdef FEA_CLUSTER_TRACE
+// per system: start / end of its solve (ns, %globaltimer), SM of rank 0, cluster size and iterations -- the
+// timeline of a batch (tools/cluster_timeline.py); dumped by pcg_cluster_profile_dump to $FEA_CLUSTER_TRACE_FILE
+__device__ unsigned long long g_cl_trace[8192][4];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #endif
 #ifdef FEA_CLUSTER_DEBUG
 #define DBG(...) do { if (rank == 0 && tid == 0) printf(__VA_ARGS__); } while (0)
@@ -438,6 +449,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     if (P.sc.done[s]) { cluster.sync(); continue; }   // empty / zero-load systems (init_scalars)
 #ifdef FEA_CLUSTER_ACCOUNT
     const long long acc_t1 = clock64();
+#endif
+#ifdef FEA_CLUSTER_TRACE
+    const unsigned long long tr_t0 = gtime();
 #endif
 
     // ---- geometry of the system inside the cluster ----------------------------------------------
@@ -1040,6 +1054,16 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       for (int i = 0; i < 3; ++i)
         if (nb[i]) atomicAdd(cnt + i, (unsigned long long)(nb[i] * (long long)(iters + 1 + refine_round)));
     }
+#ifdef FEA_CLUSTER_TRACE
+    if (rank == 0 && tid == 0 && s < 8192) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_cl_trace[s][0] = tr_t0;
+      g_cl_trace[s][1] = gtime();
+      g_cl_trace[s][2] = ((unsigned long long)CL << 32) | smid;
+      g_cl_trace[s][3] = (unsigned long long)iters;
+    }
+#endif
     if (rank == 0 && tid == 0) {
       P.sc.iters[s] = iters;
       P.sc.status[s] = status;
@@ -1087,7 +1111,9 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int
   cfg->numAttrs = 1;
 }
 
-// Co-resident clusters of `cl` CTAs (0 = path unavailable on this device).
+// Co-resident clusters of `cl` CTAs (0 = path unavailable on this device).  The occupancy API accounts for the
+// GPC structure (B200: 74 / 45 / 33 clusters of 2 / 3 / 4 CTAs, i.e. 148 / 135 / 132 SMs -- the same numbers a probe
+// kernel that timestamps its clusters' arrivals measures), so a persistent grid of this size has no pending CTAs.
 int pcg_cluster_capacity(Ctx& c, int cl) {
   const int slot = cl;
   if (c.cluster_capacity[slot] >= 0) return c.cluster_capacity[slot];
@@ -1108,8 +1134,24 @@ int pcg_cluster_capacity(Ctx& c, int cl) {
   return n;
 }
 
+#if defined(FEA_CLUSTER_TRACE) && !defined(FEA_CLUSTER_ACCOUNT)
+#error "FEA_CLUSTER_TRACE needs FEA_CLUSTER_ACCOUNT (the dump hook)"
+#endif
 #if defined(FEA_CLUSTER_PROFILE) || defined(FEA_CLUSTER_ACCOUNT)
 void pcg_cluster_profile_dump() {
+#ifdef FEA_CLUSTER_TRACE
+  if (const char* path = getenv("FEA_CLUSTER_TRACE_FILE")) {
+    static unsigned long long tr[8192][4];
+    cudaMemcpyFromSymbol(tr, g_cl_trace, sizeof(tr));
+    if (FILE* f = fopen(path, "w")) {
+      for (int i = 0; i < 8192; ++i)
+        if (tr[i][1]) fprintf(f, "%d %llu %llu %llu %llu %llu\n", i, tr[i][0], tr[i][1], tr[i][2] >> 32, tr[i][2] & 0xffffffffull, tr[i][3]);
+      fclose(f);
+    }
+    static unsigned long long zero[8192][4];
+    cudaMemcpyToSymbol(g_cl_trace, zero, sizeof(zero));
+  }
+#endif
   unsigned long long h[16];
   cudaMemcpyFromSymbol(h, g_cl_prof, sizeof(h));
 #ifdef FEA_CLUSTER_ACCOUNT
