@@ -6,7 +6,9 @@ import re
 import sys
 from collections import OrderedDict
 
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
+import gzip, io
+_f = io.TextIOWrapper(gzip.open(sys.argv[1])) if sys.argv[1].endswith(".gz") else open(sys.argv[1])
+rows = [r for r in csv.reader(_f) if len(r) > 10 and r[0].isdigit()]
 agg = OrderedDict()
 for r in rows:
     name = re.sub(r"\(.*", "", r[4])
