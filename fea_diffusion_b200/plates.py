@@ -47,6 +47,23 @@ MATERIALS = [
 ]
 
 
+_TREE_CACHE = None
+
+
+def _tree_cache():
+    """joblib.Memory in a per-process temporary directory (removed at exit)."""
+    global _TREE_CACHE
+    if _TREE_CACHE is None:
+        import atexit
+        import shutil
+        import tempfile
+        from joblib import Memory
+        d = tempfile.mkdtemp(prefix="fea_agglomerative_")
+        atexit.register(shutil.rmtree, d, True)
+        _TREE_CACHE = Memory(location=d, verbose=0)
+    return _TREE_CACHE
+
+
 class GeometryRejected(Exception):
     pass
 
@@ -355,7 +372,10 @@ class PlateGenerator:
         coors = self.mesh[0]
         pts = np.concatenate([coors, np.zeros((len(coors), 1))], axis=1)
         n_regions = self.random.randint(*self.num_regions)
-        lab = Agglomerative(n_clusters=n_regions, linkage=link).fit_predict(pts)
+        # the merge tree depends on the points and the linkage only, the number of regions only on where it is cut:
+        # scikit-learn's own `memory` option keeps the tree (O(n^2) to build: seconds for a 10 k-vertex plate)
+        # between the candidate conditions of a plate -- same labels, one tree per (plate, linkage)
+        lab = Agglomerative(n_clusters=n_regions, linkage=link, memory=_tree_cache()).fit_predict(pts)
         return [coors[lab == r] for r in range(n_regions)]
 
     def _regions_lloyd(self) -> List[np.ndarray]:
