@@ -47,7 +47,7 @@ struct Ctx {
   int prio_lo = 0, prio_hi = 0;        // least / most urgent stream priority this context may use
   cudaStream_t prio_streams[9] = {};   // (cluster_prio knob) stream of class k at its chosen urgency, made on demand
   int prio_streams_key = 0;
-  int cluster_prio = 0;                // tuning knob: decimal digit k (from the right) = urgency 1..6 of class k, 0 = default rule
+  int cluster_prio = 0;                // tuning knob: decimal digit k (from the right) = urgency 1 (the device's least urgent level) .. 6 of class k, 0 = default rule
   int spmv_variant = 0;  // tuning knob (env FEA_SPMV_VARIANT), 0 = default
   int64_t launches = 0;  // kernels launched (bookkeeping for bench.py's gpu_launches)
 };

@@ -17,6 +17,7 @@
 //     an edge force divided by max(#region vertices, 1) (fea_analysis.py:99-105), times the number
 //     of LHS terms (F2).
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -336,9 +337,20 @@ __global__ void k_cell_region_combos(const int64_t* __restrict__ cell_off, const
 // ===========================================================================
 // A-19 classifier: parts of the stiffness mesh (cells joined through shared edges) with fewer than
 // two fixed vertices, and active vertices without any stiffness cell.  Lock-free union-find over
-// the cells (roots are hooked with atomicCAS, larger index under smaller), so the partition -- and
-// with it every count -- is independent of the execution order.
+// the cells (roots are hooked with atomicCAS in a fixed pseudo-random order of the indices), so the
+// partition -- and with it every count -- is independent of the execution order.
 // ===========================================================================
+// Which of two roots goes under the other is decided by a fixed pseudo-random order of the cell indices (a
+// bijective hash), not by the indices themselves: cells are numbered along the mesh, and "larger index under
+// smaller" with thousands of concurrent unions of neighbouring cells builds chains as long as a strip of the mesh
+// (measured: 27 k cycles per union on a 9 k-cell plate), a random order keeps them logarithmic.
+__device__ __forceinline__ uint32_t cc_prio(int x) {
+  uint32_t h = (uint32_t)x * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA77u;
+  h ^= h >> 13;
+  return h;
+}
 __device__ __forceinline__ int cc_find(int32_t* parent, int x) {
   for (;;) {
     const int p = __ldcg(parent + x);
@@ -353,7 +365,7 @@ __device__ __forceinline__ void cc_union(int32_t* parent, int a, int b) {
     a = cc_find(parent, a);
     b = cc_find(parent, b);
     if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }
+    if (cc_prio(a) < cc_prio(b)) { const int t = a; a = b; b = t; }
     const int old = atomicCAS(parent + a, a, b);
     if (old == a) return;
   }
@@ -413,11 +425,157 @@ __global__ void k_cc_count(int64_t NC, int npc, const int32_t* __restrict__ conn
   if (nfix[c] < 2) atomicAdd(floating + vsample[conn[c * npc]], 1);
 }
 
+// The same classifier for plate-sized samples: ONE CTA per sample, parent links and fixed-vertex counts of the
+// sample's cells in shared memory (8 bytes per cell), so the pointer chasing of the union-find costs shared-memory
+// instead of L2 latencies (measured on the 400-sample bench batch: 2.0 ms with the global-memory kernels above,
+// which remain for samples too large for shared memory).  Counts are independent of the execution order.
+__device__ __forceinline__ int cc_find_s(volatile int32_t* parent, int x) {
+  for (;;) {
+    const int p = parent[x];
+    if (p == x) return x;
+    const int gp = parent[p];
+    if (gp != p) parent[x] = gp;
+    x = p;
+  }
+}
+template <int NPC>
+__global__ void __launch_bounds__(1024) k_cc_sample(const int64_t* __restrict__ cell_off, const int64_t* __restrict__ vtx_off,
+                                                    const int32_t* __restrict__ conn, const int32_t* __restrict__ cell_dreg,
+                                                    const uint8_t* __restrict__ fixed, const int32_t* __restrict__ inc_ptr,
+                                                    const int32_t* __restrict__ inc, int32_t* __restrict__ floating,
+                                                    int32_t* __restrict__ empty_cnt) {
+  extern __shared__ int32_t cc_sm[];
+  const int s = blockIdx.x;
+  const int64_t c0 = cell_off[s], v0 = vtx_off[s];
+  const int nc = (int)(cell_off[s + 1] - c0), nv = (int)(vtx_off[s + 1] - v0);
+  int32_t* parent = cc_sm;
+  int32_t* nfix = cc_sm + nc;
+  __shared__ int32_t tot[2];
+#ifdef FEA_CC_PROFILE
+  long long tp[6];
+  tp[0] = clock64();
+#define CC_T(i) do { __syncthreads(); tp[i] = clock64(); } while (0)
+#else
+#define CC_T(i) do { } while (0)
+#endif
+  if (threadIdx.x < 2) tot[threadIdx.x] = 0;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    parent[c] = cell_dreg[c0 + c] >= 0 ? c : -1;
+    nfix[c] = 0;
+  }
+  __syncthreads();
+  CC_T(1);
+  // Two stiffness cells share an edge iff they share two vertices.  One thread per (cell c, corner a): the other
+  // cells around the corner's vertex v come from v's incidence list; a cell c2 > c that also holds one of the two
+  // edge neighbours w of v in c shares the edge (v, w) with c, which is handled at its smaller end (v < w).  All
+  // loads of a step are issued together (up to 8 incidence entries, then the corners of those cells): four
+  // dependent round trips per thread.  (A thread per vertex with the cells' corners in local arrays diverges in
+  // its pair loop and ran no faster than k_cc_union's search, 1.0 - 1.2 M cycles per 9 k-cell sample.)
+  for (int base = 0; base < nc * NPC; base += blockDim.x) {
+    // the lanes of a warp leave the union loops below at different times: without an explicit reconvergence point
+    // they run the rest of this loop one lane at a time (measured with ncu: 20 x the warp instructions, 2 M cycles
+    // per 9 k-cell sample instead of 0.1 M)
+    __syncwarp();
+    const int gid = base + threadIdx.x;
+    const int c = gid / NPC, a = gid - c * NPC;
+    if (gid < nc * NPC && parent[c] >= 0) {
+      const int32_t* cc = conn + (c0 + c) * NPC;
+      const int v = cc[a], nxt = cc[(a + 1) % NPC], prv = cc[(a + NPC - 1) % NPC];
+      const int b = inc_ptr[v], e = inc_ptr[v + 1];
+      for (int m0 = b; m0 < e; m0 += 8) {
+        int ent[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) ent[m] = m0 + m < e ? inc[m0 + m] : -1;
+        int oth[8][NPC - 1];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int64_t c2 = ent[m] >> 2;
+          const bool use = ent[m] >= 0 && (int)(c2 - c0) > c;         // every pair once
+#pragma unroll
+          for (int q = 1; q < NPC; ++q) oth[m][q - 1] = use ? conn[c2 * NPC + ((ent[m] & 3) + q) % NPC] : -1;
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          bool adj = false;
+#pragma unroll
+          for (int q = 0; q < NPC - 1; ++q)
+            adj = adj || (oth[m][q] > v && (oth[m][q] == nxt || oth[m][q] == prv));
+          if (adj) {
+            int x = c, y = (int)((ent[m] >> 2) - c0);
+            for (;;) {                                   // lock-free union (cc_prio decides which root stays)
+              x = cc_find_s(parent, x);
+              y = cc_find_s(parent, y);
+              if (x == y) break;
+              if (cc_prio(x) < cc_prio(y)) { const int t = x; x = y; y = t; }
+              if (atomicCAS(parent + x, x, y) == x) break;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  CC_T(2);
+  for (int c = threadIdx.x; c < nc; c += blockDim.x)
+    if (parent[c] >= 0) parent[c] = cc_find_s(parent, c);
+  __syncthreads();
+  CC_T(3);
+  int n_empty = 0;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const int b = inc_ptr[v0 + v], e = inc_ptr[v0 + v + 1];
+    if (!fixed[v0 + v]) {
+      n_empty += b == e ? 1 : 0;
+      continue;
+    }
+    int roots[kMaxAdj], n = 0;                      // (part, vertex) pairs once each
+    for (int i = b; i < e; ++i) {
+      const int r = parent[(int)((inc[i] >> 2) - c0)];
+      bool seen = false;
+      for (int k = 0; k < n; ++k) seen = seen || roots[k] == r;
+      if (!seen && n < kMaxAdj) { roots[n++] = r; atomicAdd(nfix + r, 1); }
+    }
+  }
+  __syncthreads();
+  CC_T(4);
+  int n_float = 0;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) n_float += (parent[c] == c && nfix[c] < 2) ? 1 : 0;
+  if (n_float) atomicAdd(&tot[0], n_float);
+  if (n_empty) atomicAdd(&tot[1], n_empty);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    floating[s] = tot[0];
+    empty_cnt[s] = tot[1];
+  }
+#ifdef FEA_CC_PROFILE
+  CC_T(5);
+  if (threadIdx.x == 0 && (s == 0 || s == 200))
+    printf("[cc] sample %d nc %d nv %d: init %lld union %lld flatten %lld vertices %lld count %lld cycles\n", s, nc, nv,
+           tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
+#endif
+}
+
 __global__ void k_merge_err(const int32_t* __restrict__ src, int32_t* __restrict__ dst) { *dst = *src; }
 
 cudaError_t launch_classify(Batch& b, int32_t* d_floating, int32_t* d_empty) {
   cudaStream_t st = b.ctx->stream;
   const int T = 256;
+  {   // plate-sized samples: one CTA per sample, union-find in shared memory
+    int64_t max_nc = 0;
+    for (int s = 0; s < b.ns; ++s) max_nc = std::max(max_nc, b.cell_off[s + 1] - b.cell_off[s]);
+    const size_t bytes = (size_t)max_nc * 8;
+    if (b.ns > 0 && max_nc > 0 && bytes <= 200 * 1024) {
+      cudaError_t e;
+      if (b.npc == 3) {
+        if ((e = cudaFuncSetAttribute(k_cc_sample<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        k_cc_sample<3><<<b.ns, 1024, bytes, st>>>(b.d_cell_off, b.d_vtx_off, b.conn, b.cell_dreg, b.fixed, b.inc_ptr, b.inc, d_floating, d_empty);
+      } else {
+        if ((e = cudaFuncSetAttribute(k_cc_sample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        k_cc_sample<4><<<b.ns, 1024, bytes, st>>>(b.d_cell_off, b.d_vtx_off, b.conn, b.cell_dreg, b.fixed, b.inc_ptr, b.inc, d_floating, d_empty);
+      }
+      b.ctx->launches += 1;
+      return cudaGetLastError();
+    }
+  }
   cudaMemsetAsync(d_floating, 0, sizeof(int32_t) * b.ns, st);
   cudaMemsetAsync(d_empty, 0, sizeof(int32_t) * b.ns, st);
   int32_t *parent = nullptr, *nfix = nullptr;

@@ -559,7 +559,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
         digit %= 10;
         if (digit > 0) {
           if (!c.prio_streams[k]) {
-            const int pr = c.prio_lo - (digit - 1) < c.prio_hi ? c.prio_hi : c.prio_lo - (digit - 1);
+            const int pr = -(digit - 1) < c.prio_hi ? c.prio_hi : -(digit - 1);   // absolute: 1 = the device's least urgent level
             cudaStreamCreateWithPriority(&c.prio_streams[k], cudaStreamNonBlocking, pr);
           }
           a = k - 1;                                 // join-event slot of this class
