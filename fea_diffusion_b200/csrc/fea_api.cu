@@ -408,7 +408,7 @@ int fea_batch_assemble(fea_batch* hb) {
   CK(ctx, dalloc(b, &b.val, b.n_blocks * 4));
   CK(ctx, dalloc(b, &b.col, b.n_blocks));
   CK(ctx, dalloc(b, &b.dscale, b.NBR * 2));
-  CK(ctx, dalloc(b, &b.dcoup, b.NBR));
+  CK(ctx, dalloc(b, &b.scoup, b.NBR));
   CK(ctx, dalloc(b, &b.x, b.NBR * 2));
   CK(ctx, dalloc(b, &b.rp, b.NBR * 4));
   CK(ctx, dalloc(b, &b.q, b.NBR * 2));

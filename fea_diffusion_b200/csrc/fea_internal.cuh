@@ -124,8 +124,11 @@ struct Batch {
   int64_t n_blocks = 0;
   double* val = nullptr;         // [n_blocks*4]  one 32-byte block (k00,k01,k10,k11) per entry
   int32_t* col = nullptr;        // [n_blocks]
-  double* dscale = nullptr;      // [NBR*2] 1/sqrt(diag)
-  double* dcoup = nullptr;       // [NBR] scaled x-y coupling of the diagonal block
+  // Block scaling S (2x2 per vertex): Khat = S^T K S has IDENTITY diagonal blocks, so plain CG on Khat is
+  // 2x2-block-Jacobi PCG on K at no cost per iteration.  With the Cholesky factor L of a vertex's diagonal
+  // block, S = L^-T = [[i00, i10], [0, i11]]: dscale = (i00, i11), scoup = i10.
+  double* dscale = nullptr;      // [NBR*2] (i00, i11)
+  double* scoup = nullptr;       // [NBR] i10
   int32_t max_row_blocks = 0;
   // solver vectors: x, q [NBR*2]; rp [NBR*4] = one 32-byte record (r.x, r.y, p.x, p.y) per block
   // row, so that a neighbour's residual and search direction arrive with ONE 256-bit gather

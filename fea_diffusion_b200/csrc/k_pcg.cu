@@ -135,9 +135,8 @@ __global__ void __launch_bounds__(kT, MINB) k_pcg_spmv(const PcgPtrs* __restrict
   const uint64_t pol_m = HINT ? l2_policy_evict_first() : 0, pol_v = HINT ? l2_policy_evict_last() : 0;
   // own row: p_i and the diagonal block [[1, a], [a, 1]]
   const d4 own = HINT ? ld_nc_d4_hint(rp + row, pol_v) : ld_nc_d4(rp + row);
-  const double dc = __ldg(P.dcoup + row);
   const double2 pn = make_double2(fma(beta, own.z, own.x), fma(beta, own.w, own.y));
-  double a0 = fma(dc, pn.y, pn.x), a1 = fma(dc, pn.x, pn.y);
+  double a0 = pn.x, a1 = pn.y;   // the diagonal block of Khat is the identity
 #pragma unroll 1
   for (int j0 = 0; j0 < L; j0 += U) {
     int c[U];
@@ -240,7 +239,8 @@ __global__ void __launch_bounds__(kT) k_pcg_update(const PcgPtrs* __restrict__ P
 __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restrict__ Pp,
                                                           const int32_t* __restrict__ vertex_of_row,
                                                           const double* __restrict__ rhs,
-                                                          const double* __restrict__ dscale, int monitor) {
+                                                          const double* __restrict__ dscale,
+                                                          const double* __restrict__ scoup, int monitor) {
   __shared__ double sm[kT / 32];
   const PcgPtrs& P = *Pp;
   const int cta = blockIdx.x;
@@ -261,8 +261,7 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
   const int32_t* __restrict__ cp = P.col + base + lane;
   const double2* __restrict__ x = P.x;
   const double2 xi = x[row];
-  const double dc = __ldg(P.dcoup + row);
-  double a0 = fma(dc, xi.y, xi.x), a1 = fma(dc, xi.x, xi.y);
+  double a0 = xi.x, a1 = xi.y;   // the diagonal block of Khat is the identity
   for (int j = 0; j < L; ++j) {
     const int c = ld_stream_i32(cp + j * 32);
     const d4 k = ld_stream_d4(vt + j * 32);
@@ -278,8 +277,9 @@ __global__ void __launch_bounds__(kT) k_pcg_true_residual(const PcgPtrs* __restr
   if (monitor) rec = P.rp[row];   // keep p
   rec.x = rec.y = 0.0;
   if (v >= 0) {
-    rec.x = dscale[2 * row] * rhs[2 * (int64_t)v] - a0;
-    rec.y = dscale[2 * row + 1] * rhs[2 * (int64_t)v + 1] - a1;
+    const double b0 = rhs[2 * (int64_t)v], b1 = rhs[2 * (int64_t)v + 1];     // S^T b = L^-1 b
+    rec.x = dscale[2 * row] * b0 - a0;
+    rec.y = fma(scoup[row], b0, dscale[2 * row + 1] * b1) - a1;
   }
   P.rp[row] = rec;
   const double part = cta_sum(fma(rec.x, rec.x, rec.y * rec.y), sm);
@@ -376,7 +376,8 @@ __global__ void k_store_params(PcgPtrs P, PcgPtrs* __restrict__ dst) {
 __global__ void __launch_bounds__(kT) k_pcg_init_vectors(const PcgPtrs* __restrict__ Pp,
                                                          const int32_t* __restrict__ vertex_of_row,
                                                          const double* __restrict__ rhs,
-                                                         const double* __restrict__ dscale) {
+                                                         const double* __restrict__ dscale,
+                                                         const double* __restrict__ scoup) {
   __shared__ double sm[kT / 32];
   const PcgPtrs& P = *Pp;
   const int s = P.sys_of_cta[blockIdx.x];
@@ -384,7 +385,10 @@ __global__ void __launch_bounds__(kT) k_pcg_init_vectors(const PcgPtrs* __restri
   const int64_t row = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int v = vertex_of_row[row];
   double2 b = make_double2(0.0, 0.0);
-  if (v >= 0) b = make_double2(dscale[2 * row] * rhs[2 * (int64_t)v], dscale[2 * row + 1] * rhs[2 * (int64_t)v + 1]);
+  if (v >= 0) {   // S^T b = L^-1 b
+    const double b0 = rhs[2 * (int64_t)v], b1 = rhs[2 * (int64_t)v + 1];
+    b = make_double2(dscale[2 * row] * b0, fma(scoup[row], b0, dscale[2 * row + 1] * b1));
+  }
   const double2 z = make_double2(0.0, 0.0);
   d4 rec;
   rec.x = b.x;
@@ -434,7 +438,6 @@ static PcgPtrs make_ptrs(Batch& b, int max_iter) {
   P.slice_ptr = b.slice_ptr;
   P.val = (const d4*)b.val;
   P.col = b.col;
-  P.dcoup = b.dcoup;
   P.x = (double2*)b.x;
   P.rp = (d4*)b.rp;
   P.q = (double2*)b.q;
@@ -531,7 +534,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
   k_store_params<<<1, 32, 0, st>>>(P, dP);
   cudaMemsetAsync(b.sc.n_done, 0, sizeof(int32_t), st);
   cudaMemsetAsync(b.sc.arrive, 0, sizeof(int32_t) * 2 * b.ns, st);
-  if (ncta) k_pcg_init_vectors<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale);
+  if (ncta) k_pcg_init_vectors<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, b.scoup);
   k_pcg_init_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, b.empty, rtol);
   launches += 3;
   if (n_cluster > 0) {  // systems that fit on chip: one per cluster, pulled from a queue
@@ -594,7 +597,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       // residual replacement: check converged systems against their true residual, reopen failures
       int32_t* d_reopened = b.cl_counter + 9;
       cudaMemsetAsync(d_reopened, 0, sizeof(int32_t), st);
-      k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, 0);
+      k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, b.scoup, 0);
       k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, d_reopened, round <= c.refine_rounds ? 1 : 0, 0);
       k_compact_active<<<1, 1024, 0, st>>>(dP);
       launches += 3;
@@ -636,7 +639,7 @@ cudaError_t run_pcg(Batch& b, double rtol, int max_iter) {
       }
       launches += (int64_t)per_iter * kChunk + 1;
       if ((k - k_first + 1) % mon_chunks == 0) {   // periodic true-residual monitor (see k_pcg_true_residual)
-        k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, 1);
+        k_pcg_true_residual<<<ncta, kT, 0, st>>>(dP, b.vertex_of_row, b.rhs, b.dscale, b.scoup, 1);
         k_pcg_refine_scalars<<<(b.ns + 3) / 4, 128, 0, st>>>(dP, nullptr, 0, 1);
         launches += 2;
       }
@@ -743,6 +746,7 @@ void pcg_release(Ctx& c) {
 // ---------------------------------------------------------------------------
 __global__ void k_unscale_scatter(int64_t NV, const int32_t* __restrict__ vsample,
                                   const int32_t* __restrict__ row_of_vertex, const double* __restrict__ dscale,
+                                  const double* __restrict__ scoup,
                                   const double2* __restrict__ x, const int32_t* __restrict__ status,
                                   double2* __restrict__ u) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -755,7 +759,7 @@ __global__ void k_unscale_scatter(int64_t NV, const int32_t* __restrict__ vsampl
     const int row = row_of_vertex[v];
     if (row >= 0) {
       const double2 xv = x[row];
-      o = make_double2(dscale[2 * (int64_t)row] * xv.x, dscale[2 * (int64_t)row + 1] * xv.y);
+      o = make_double2(fma(scoup[row], xv.y, dscale[2 * (int64_t)row] * xv.x), dscale[2 * (int64_t)row + 1] * xv.y);   // u = S xhat
     }
   }
   u[v] = o;
@@ -804,7 +808,7 @@ cudaError_t launch_finalize(Batch& b) {
   cudaStream_t st = b.ctx->stream;
   const int T = 256;
   if (b.NV)
-    k_unscale_scatter<<<(unsigned)((b.NV + T - 1) / T), T, 0, st>>>(b.NV, b.vsample, b.row_of_vertex, b.dscale,
+    k_unscale_scatter<<<(unsigned)((b.NV + T - 1) / T), T, 0, st>>>(b.NV, b.vsample, b.row_of_vertex, b.dscale, b.scoup,
                                                                    (const double2*)b.x, b.sc.status, (double2*)b.u);
   k_minmax<<<b.ns, 256, 0, st>>>(b.d_vtx_off, (const double2*)b.u, b.ranges);
   k_relres<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.rz_last, b.sc.rz0, b.relres);
@@ -816,8 +820,8 @@ cudaError_t launch_finalize(Batch& b) {
 // ---------------------------------------------------------------------------
 __global__ void k_spmv_load(int64_t NBR, const int32_t* __restrict__ vertex_of_row,
                             const int32_t* __restrict__ vrank, int64_t v0, int64_t v1,
-                            const double* __restrict__ dscale, const double* __restrict__ xin,
-                            d4* __restrict__ rp) {
+                            const double* __restrict__ dscale, const double* __restrict__ scoup,
+                            const double* __restrict__ xin, d4* __restrict__ rp) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= NBR) return;
   const int v = vertex_of_row[row];
@@ -825,7 +829,10 @@ __global__ void k_spmv_load(int64_t NBR, const int32_t* __restrict__ vertex_of_r
   if (v >= v0 && v < v1) {
     const int rk = vrank[v];
     const double s0 = dscale[2 * row], s1 = dscale[2 * row + 1];
-    o = make_double2(s0 > 0 ? xin[2 * rk] / s0 : 0.0, s1 > 0 ? xin[2 * rk + 1] / s1 : 0.0);
+    if (s0 > 0 && s1 > 0) {   // xhat = S^-1 x
+      const double x1 = xin[2 * rk + 1] / s1;
+      o = make_double2((xin[2 * rk] - scoup[row] * x1) / s0, x1);
+    }
   }
   d4 rec;
   rec.x = o.x;
@@ -835,8 +842,8 @@ __global__ void k_spmv_load(int64_t NBR, const int32_t* __restrict__ vertex_of_r
 }
 __global__ void k_spmv_store(int64_t NBR, const int32_t* __restrict__ vertex_of_row,
                              const int32_t* __restrict__ vrank, int64_t v0, int64_t v1,
-                             const double* __restrict__ dscale, const double2* __restrict__ q,
-                             double* __restrict__ yout) {
+                             const double* __restrict__ dscale, const double* __restrict__ scoup,
+                             const double2* __restrict__ q, double* __restrict__ yout) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= NBR) return;
   const int v = vertex_of_row[row];
@@ -844,8 +851,9 @@ __global__ void k_spmv_store(int64_t NBR, const int32_t* __restrict__ vertex_of_
     const int rk = vrank[v];
     const double s0 = dscale[2 * row], s1 = dscale[2 * row + 1];
     const double2 qv = q[row];
-    yout[2 * rk] = s0 > 0 ? qv.x / s0 : 0.0;
-    yout[2 * rk + 1] = s1 > 0 ? qv.y / s1 : 0.0;
+    const double y0 = s0 > 0 ? qv.x / s0 : 0.0;                       // y = S^-T q
+    yout[2 * rk] = y0;
+    yout[2 * rk + 1] = s1 > 0 ? (qv.y - scoup[row] * y0) / s1 : 0.0;
   }
 }
 __global__ void k_spmv_scalars(int ns, SysScalars sc, const int32_t* __restrict__ cta_first,
@@ -873,10 +881,10 @@ cudaError_t launch_plain_spmv(Batch& b, int32_t s, const double* d_x, double* d_
   k_store_params<<<1, 32, 0, st>>>(make_ptrs(b, 1 << 30), dP);
   k_spmv_scalars<<<(b.ns + T - 1) / T, T, 0, st>>>(b.ns, b.sc, b.cta_first, b.cta_count, b.partB);
   k_compact_active<<<1, 1024, 0, st>>>(dP);
-  k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, d_x, (d4*)b.rp);
+  k_spmv_load<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, b.scoup, d_x, (d4*)b.rp);
   cudaMemsetAsync(b.sc.arrive, 0, sizeof(int32_t) * 2 * b.ns, st);
   pick_spmv(b.ctx->spmv_variant)<<<ncta, kT, 0, st>>>(dP, 0);
-  k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, (const double2*)b.q, d_y);
+  k_spmv_store<<<g, T, 0, st>>>(b.NBR, b.vertex_of_row, b.vrank, v0, v1, b.dscale, b.scoup, (const double2*)b.q, d_y);
   return cudaGetLastError();
 }
 

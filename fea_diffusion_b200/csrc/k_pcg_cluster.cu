@@ -96,6 +96,14 @@ static_assert(kClU % 4 == 0 && kClUs % 4 == 0, "gather codes are fetched four at
 #ifndef FEA_CL_TMEM
 #define FEA_CL_TMEM 1
 #endif
+// The scaled diagonal block is the identity, so a row's product starts from q = p.  FEA_CL_DCS = 1 keeps the
+// per-row coupling array of the point-Jacobi layout (now all zeros) and its two FMAs in the SpMV: measured
+// FASTER than starting from p directly (27.5 against 28.0 ms per 400-system batch, 28.4 ms with the zero in one
+// shared scalar) -- ptxas allocates registers differently (16 / 8 bytes of spill traffic instead of 32 / 48) and
+// starts the first loads of a slice earlier.  Same bits in all three builds.
+#ifndef FEA_CL_DCS
+#define FEA_CL_DCS 1
+#endif
 #ifndef FEA_CL_ONE_DIV
 #define FEA_CL_ONE_DIV 1
 #endif
@@ -123,6 +131,7 @@ struct ClHeader {                 // start of the dynamic shared memory of every
   // table a slower warp is still summing, nor complete bytes on a phase that has not opened yet
   alignas(32) double partA[2][kClMax * kClW * 4];
   double partB[kClMax * kClW];    // r.r partials of the true-residual passes (check / monitor / refinement)
+  double rz_zero;                 // (A/B build FEA_CL_DCS == 2) 0.0
   double rz_monitor;              // smallest true r.r any monitor pass has seen
   double tol2;                    // rtol^2 * r0.r0 of the current system (tightened by an extended-precision round)
   int32_t mon_strikes;            // consecutive monitor passes without a 4x gain on rz_monitor
@@ -371,11 +380,8 @@ __device__ __noinline__ double dd_residual_rows(const PcgPtrs* Pp, int64_t my_ro
     const int L = P.slice_len[row >> 5];
     const int64_t base = P.slice_ptr[row >> 5] + lane;
     const double2 b = P.sb[row], xh = __ldcg(P.x + row), xl = __ldcg(P.xlo + row);
-    const double a = P.dcoup[row];
     dd2 r0{b.x, 0.0}, r1{b.y, 0.0};
-    r0 = dd_add(r0, -xh.x, -xl.x);            // diagonal block [[1, a], [a, 1]]
-    r0 = dd_msub(r0, a, xh.y, xl.y);
-    r1 = dd_msub(r1, a, xh.x, xl.x);
+    r0 = dd_add(r0, -xh.x, -xl.x);            // the scaled diagonal block is the identity
     r1 = dd_add(r1, -xh.y, -xl.y);
 #pragma unroll 1
     for (int j = 0; j < L; ++j) {
@@ -522,7 +528,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     cluster.sync();                                                // #1: send_from[] complete
 
     // ---- layout of the shared memory (depends on the halo and send-list sizes) -------------------
-    //   header | send list [n_send] u32 | p: own rows [Rc] + halo [H] double2 | dcoup [Rc] f64 |
+    //   header | send list [n_send] u32 | p: own rows [Rc] + halo [H] double2 |
     //   gather codes of all owned slices (u16 index into p) | 2x2 blocks of the resident slices
     if (tid < kCl) {
       int off = 0;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       int ent = 0;
       for (int i = 0; i < kClSlices; ++i) { h->s_aoff[i] = ent; ent += (h->s_len[i] + 3) / 4 * 128; }
       const int off_pbuf = kHdr + (4 * S + 127) / 128 * 128;
-      const int mat0 = (off_pbuf + 16 * (Rc + H) + 8 * Rc + 127) / 128 * 128;
+      const int mat0 = (off_pbuf + 16 * (Rc + H) + (FEA_CL_DCS == 1 ? 8 * Rc : 0) + 127) / 128 * 128;
       int off = (ent * 2 + 127) / 128 * 128;
       const int fit = (mat0 + off <= kClSmemBytes - kClTmpBytes && Rc + H <= 0xffff && H <= P.cl_halo_cap) ? 1 : 0;
       h->off_pbuf = off_pbuf;
@@ -573,7 +579,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
     }
     const int off_pbuf = h->off_pbuf, mat0 = h->mat0;
     double2* pbuf = reinterpret_cast<double2*>(smem + off_pbuf);   // [Rc] published p + [H] halo
-    double* dcs = reinterpret_cast<double*>(pbuf + Rc + H);        // [Rc] diagonal-block couplings
+#if FEA_CL_DCS == 1
+    double* dcs = reinterpret_cast<double*>(pbuf + Rc + H);        // (A/B build) [Rc] zeros read like the former diagonal couplings
+#endif
     const uint32_t pbuf_a = smem_u32(pbuf);
     uint16_t* sa_all = reinterpret_cast<uint16_t*>(smem + mat0);
     const uint32_t* sendl = reinterpret_cast<const uint32_t*>(smem + kHdr);
@@ -667,7 +675,9 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         const d4 rec = P.rp[my_row0 + lr];   // r0 = S b (k_pcg_init_vectors)
         r[k] = make_double2(rec.x, rec.y);
         pbuf[lr] = r[k];                     // first direction p = r
-        dcs[lr] = P.dcoup[my_row0 + lr];
+#if FEA_CL_DCS == 1
+        dcs[lr] = 0.0;
+#endif
       }
     }
 #ifdef FEA_CLUSTER_PROFILE
@@ -683,6 +693,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
       h->it_limit = P.max_iter;
       h->rz_monitor = inf;                    // smallest true r.r found by a monitor pass
       h->mon_strikes = 0;
+      h->rz_zero = 0.0;
     }
     __syncthreads();
     int iters = 0, status = FEA_SAMPLE_NOT_RUN;
@@ -740,10 +751,19 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
         const int ls = warp + kClW * k;
         double a0 = 0.0, a1 = 0.0;
         if (ls < my_sl) {
-          const double2 pk = pbuf[tid + kClT * k];
+          const double2 pk = pbuf[tid + kClT * k];   // the diagonal block of Khat is the identity
+#if FEA_CL_DCS == 1
           const double dck = dcs[tid + kClT * k];
           a0 = fma(dck, pk.y, pk.x);
           a1 = fma(dck, pk.x, pk.y);
+#elif FEA_CL_DCS == 2
+          const double dck = h->rz_zero;
+          a0 = fma(dck, pk.y, pk.x);
+          a1 = fma(dck, pk.x, pk.y);
+#else
+          a0 = pk.x;
+          a1 = pk.y;
+#endif
           const int L = h->s_len[ls];
           const int off = h->s_off[ls];
           const uint2* sa = reinterpret_cast<const uint2*>(sa_all + h->s_aoff[ls]) + lane;   // 4 codes per load

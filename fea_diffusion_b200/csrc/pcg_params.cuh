@@ -15,7 +15,6 @@ struct PcgPtrs {
   const int64_t* slice_ptr;
   const d4* val;
   const int32_t* col;
-  const double* dcoup;
   double2* x;
   d4* rp;            // (r.x, r.y, p.x, p.y) per block row; p = direction of the PREVIOUS iteration
   double2* q;
