@@ -2,7 +2,7 @@
 """bench.py -- plate-condition FEA solves/s on N B200s (BASELINE.json metric).
 
 One "step" = one pass of the hot path over one batch of synthetic plate-condition samples:
-assembly + Dirichlet elimination + Jacobi-PCG solve (all load steps of a condition are t_k
+assembly + Dirichlet elimination + block-Jacobi PCG solve (all load steps of a condition are t_k
 multiples of one solve) + ranges + the two 64x64 displacement images.
 Default workload = BASELINE.json configs[1]: 100 plates x 4 conditions x 10 loaded steps
 (steps_per_condition 11), default mesh density, image_size 64.

@@ -230,9 +230,9 @@ int  fea_ctx_kernel_launches(fea_ctx* ctx, int64_t* out);
  *            equation map (problem.set_bcs, fea_analysis.py:422; A-9).
  * assemble : element stiffness (dw_lin_elastic, fea_analysis.py:153-160,302-310; A-4/A-5),
  *            matrix graph (sfepy mesh_graph inside problem.solve, :437; A-11),
- *            value assembly with Dirichlet rows/cols dropped (A-10), Jacobi scaling,
+ *            value assembly with Dirichlet rows/cols dropped (A-10), 2x2 block-Jacobi scaling,
  *            load vector (dw_point_load, :338-344).
- * solve    : Jacobi-preconditioned fp64 CG of every sample (on chip, one sample per thread-block
+ * solve    : block-Jacobi-preconditioned fp64 CG of every sample (on chip, one sample per thread-block
  *            cluster, or lock-step streaming kernels for large systems); replaces
  *            Newton + ScipyDirect + SimpleTimeSteppingSolver (:371-375, 425-439):
  *            one solve at t = 1, load steps are t_k multiples of it (F5).
@@ -257,7 +257,8 @@ int  fea_batch_destroy(fea_batch* b);
 /* u [n_vertices*2] final-step displacement, zeros at fixed DOFs (A-15), NaN for EMPTY_ROW
  * samples; ranges [n_samples*4] = (min ux, max ux, min uy, max uy) of the final step;
  * iters/status [n_samples]; relres [n_samples] = sqrt(r.r / r0.r0) of the TRUE residual
- * r = S (b - K u) in the Jacobi-scaled norm for converged / stagnated samples. */
+ * r = S^T (b - K u) in the block-Jacobi-scaled norm (S = inverse transposed Cholesky factors of the
+ * vertices' 2x2 diagonal blocks) for converged / stagnated samples. */
 int  fea_batch_download(fea_batch* b, double* u, double* ranges, int32_t* iters,
                         double* relres, int32_t* status);
 int  fea_batch_download_images(fea_batch* b, uint8_t* images);
