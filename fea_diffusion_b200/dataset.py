@@ -183,9 +183,11 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
         samples = [(ji, kw) for ji, j in enumerate(jobs) for kw in j["cands"][j["classified"]:]]
         if not samples:
             return
+        t_c0 = time.perf_counter()
         with ctx.create_batch_from_conditions(PackedConditions(meshes, samples)) as b:
             b.assemble()
             fl, em = b.classify()
+        stats["classify_s"] = stats.get("classify_s", 0.0) + time.perf_counter() - t_c0
         ok = (em == 0) & ((fl == 0) | (not well_posed))
         stats["candidates"] += len(samples)
         stats["rejected_ill_posed"] += int((~ok).sum())
@@ -198,6 +200,7 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
 
     def solve(jobs: List[dict], picks: List[tuple]):
         """Solves the picked (plate index, candidate index) pairs; returns one result dict per pick."""
+        t_s0 = time.perf_counter()
         meshes = [(j["coors"], j["conn"]) for j in jobs]
         samples = [(ji, jobs[ji]["cands"][k]) for ji, k in picks]
         pc = PackedConditions(meshes, samples)
@@ -212,7 +215,7 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
         with ctx.create_batch_from_conditions(pc) as b:
             b.assemble().solve(rtol, max_iter).rasterize(sz, affine, t1)
             res = b.download(images=True)
-            dev = b.setup(flags=save_meshes)
+            dev = b.setup(flags=save_meshes, counts_only=not save_meshes)
             region_imgs = b.rasterize_regions(mask)
             conn, _ = b.conn() if save_meshes else (None, None)
             strain, stress = b.cell_strain_stress(0) if want_cells else (None, None)
@@ -221,6 +224,8 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
                 # per-cell scalar renders (fea_analysis.py:539-558): component x / y of stress and strain at step 1
                 names_cf = (["stress_x", "stress_y"] if save_stress else []) + (["strain_x", "strain_y"] if save_strain else [])
                 cell_imgs, cell_rng = b.rasterize_cell_components(0, names_cf, t1)
+        t_s1 = time.perf_counter()
+        stats["solve_gpu_s"] = stats.get("solve_gpu_s", 0.0) + t_s1 - t_s0
         us = pc.split_vertices(res.u)
         out = []
         for i, (ji, k) in enumerate(picks):
@@ -245,6 +250,7 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
             elif mask[i]:
                 d["input"] = reg[-1].copy()
             out.append(d)
+        stats["solve_unpack_s"] = stats.get("solve_unpack_s", 0.0) + time.perf_counter() - t_s1
         return out
 
     def run_batch(jobs: List[dict], writers: ThreadPoolExecutor, pool):

@@ -500,13 +500,18 @@ class Batch:
         return [out[off[s]:off[s + 1]] for s in range(len(counts))]
 
     # ---- batches made from conditions -------------------------------------------------------
-    def setup(self, flags: bool = True) -> DeviceSetup:
+    def setup(self, flags: bool = True, counts_only: bool = False) -> DeviceSetup:
         """Download what the device set-up derived (parity tests, text files of the dataset)."""
         p = self.packed
         nv, nc = p.n_vertices, p.n_cells
-        fixed, creg, rhs = np.empty(nv, np.uint8), np.empty(nc, np.int8), np.empty((nv, 2))
         nreg = p.n_regions
         cnt = np.empty(int(nreg.sum()), np.int32)
+        if counts_only:      # the vertex counts of the regions alone (magnitudes.txt): nothing per vertex or cell is read back
+            self.ctx._check(self.ctx.lib.fea_batch_get_setup(self.h, None, None, None, ptr(cnt), None))
+            ro = np.concatenate([[0], np.cumsum(nreg)])
+            return DeviceSetup(fixed=None, cell_region=None, rhs=None, region_count=[cnt[ro[s]:ro[s + 1]] for s in range(p.n)],
+                               region_flags=[], D=[])
+        fixed, creg, rhs = np.empty(nv, np.uint8), np.empty(nc, np.int8), np.empty((nv, 2))
         per_v = np.diff(p.vtx_off)
         fl = np.empty(int((nreg * per_v).sum()), np.uint8) if flags else None
         self.ctx._check(self.ctx.lib.fea_batch_get_setup(self.h, ptr(fixed), ptr(creg), ptr(rhs), ptr(cnt), ptr(fl)))
