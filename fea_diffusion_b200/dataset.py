@@ -296,7 +296,10 @@ def generate_dataset(data_dir: str, num_plates: int, conditions_per_plate: int =
             pending.append(writers.submit(_write_plate, data_dir, j, out, num_steps, save_meshes, save))
         stats["batches"] += 1
 
-    first = FIRST_DRAWS * conditions_per_plate
+    # more than half of the sampler's draws are ill-posed: with 3 x conditions_per_plate candidates one
+    # plate in seven runs out and is resumed in the workers while the CUDA thread waits.  The stand-in region
+    # method is cheap enough to draw 5 x up front; the candidate STREAM of a plate, hence the dataset, is the same
+    first = (5 if region_method == "lloyd" else FIRST_DRAWS) * conditions_per_plate
     jobs_args = [(p, seed, image_size, mesh_size, 0, first, region_method) for p in mine]
     ctx = None
     with ThreadPoolExecutor(max_workers=writer_threads) as writers:
