@@ -96,13 +96,12 @@ static_assert(kClU % 4 == 0 && kClUs % 4 == 0, "gather codes are fetched four at
 #ifndef FEA_CL_TMEM
 #define FEA_CL_TMEM 1
 #endif
-// The scaled diagonal block is the identity, so a row's product starts from q = p.  FEA_CL_DCS = 1 keeps the
-// per-row coupling array of the point-Jacobi layout (now all zeros) and its two FMAs in the SpMV: measured
-// FASTER than starting from p directly (27.5 against 28.0 ms per 400-system batch, 28.4 ms with the zero in one
-// shared scalar) -- ptxas allocates registers differently (16 / 8 bytes of spill traffic instead of 32 / 48) and
-// starts the first loads of a slice earlier.  Same bits in all three builds.
+// The scaled diagonal block is the identity, so a row's product starts from q = p.  FEA_CL_DCS = 1 (A/B build)
+// keeps the per-row coupling array of the point-Jacobi layout (all zeros) and its two FMAs in the SpMV: with
+// ptxas' own unrolling of the block loops that build was the faster one (27.5 against 28.0 ms: different
+// register allocation), with the loops kept rolled both take 26.4 ms.  Same bits either way.
 #ifndef FEA_CL_DCS
-#define FEA_CL_DCS 1
+#define FEA_CL_DCS 0
 #endif
 #ifndef FEA_CL_ONE_DIV
 #define FEA_CL_ONE_DIV 1
@@ -778,6 +777,10 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
             d4 kv[4];
             double2 pj[4];
             int j = 0;
+            // (the block loops of the three storage tiers are NOT unrolled: ptxas' own unrolling by two costs spills
+            // and code -- 11 168 instead of 8 632 instructions per kernel -- and measured 27.7 against 26.4 ms per
+            // 400-system batch; the (up to 4) slices of a warp stay unrolled, their products live in registers)
+#pragma unroll 1
             for (; j + 4 <= nt; j += 4) {
               const uint2 cc = sa[(j >> 2) * 32];
               const uint32_t ga[4] = {pbuf_a + 16u * (cc.x & 0xffffu), pbuf_a + 16u * (cc.x >> 16), pbuf_a + 16u * (cc.y & 0xffffu), pbuf_a + 16u * (cc.y >> 16)};
@@ -803,6 +806,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
           } else if (off >= 0) {
             const double2* st = reinterpret_cast<const double2*>(smem + mat0 + off) + lane - nt * 32;
             const double2* sb = st + (L - nt) * 32;
+#pragma unroll 1
             for (int j = nt; j < L; j += kClU) {   // kClU gathers in flight; the tail round is predicated
               uint32_t g[kClU];
               double2 pj[kClU];
@@ -824,6 +828,7 @@ __global__ void __launch_bounds__(kClT, FEA_CL_CTAS_PER_SM) k_pcg_cluster(const 
             }
           } else {  // blocks that fit neither: streamed from global memory (L2 resident), 4 in flight
             const d4* vt = P.val + h->s_base[ls] + lane;
+#pragma unroll 1
             for (int j = nt; j < L; j += kClUs) {
               d4 kv[kClUs];
 #pragma unroll
