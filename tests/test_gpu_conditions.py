@@ -237,6 +237,33 @@ def test_staged_outputs_fetched_on_a_copy_context(ctx):
     assert reg3 is None and cls3 is None and np.array_equal(r3.u, want.u, equal_nan=True)
 
 
+def test_classifier_on_samples_too_large_for_shared_memory(ctx):
+    """The classifier keeps a plate-sized sample's union-find in shared memory (k_cc_sample); a sample with more
+    than ~25 k cells goes through the global-memory kernels (k_cc_union ...).  Both against the host classifier, on
+    a refined cantilever (77 k cells) held properly, not held at all, and with a second, unheld copy beside it."""
+    from fea_diffusion_b200.workload import large_case
+    setup, _ = large_case("cantilever", 2)
+    s = setup.sample
+    assert len(s.conn) > 60000
+    import copy
+    free = copy.deepcopy(s)
+    free.fixed[:] = False
+    two = copy.deepcopy(s)                       # the mesh twice in one sample, the copy shifted and not constrained
+    nv = len(s.coors)
+    two.coors = np.concatenate([s.coors, s.coors + np.array([10.0, 0.0])])
+    two.conn = np.concatenate([s.conn, s.conn + nv]).astype(np.int32)
+    two.cell_region = np.concatenate([s.cell_region, s.cell_region])
+    two.fixed = np.concatenate([s.fixed, np.zeros(nv, dtype=s.fixed.dtype)])
+    two.rhs = np.concatenate([s.rhs, np.zeros_like(s.rhs)])
+    samples = [s, free, two]
+    with ctx.create_batch(pack(samples)) as b:
+        b.assemble()
+        fl, em = b.classify()
+    want = [floating_components(x) for x in samples]
+    assert [(int(a), int(z)) for a, z in zip(fl, em)] == [tuple(int(v) for v in w) for w in want]
+    assert [int(a) for a in fl] == [0, 1, 1] and not em.any()
+
+
 def test_bad_tags_are_rejected(ctx):
     from fea_diffusion_b200 import FeaError
     co = np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]])
