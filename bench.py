@@ -767,7 +767,10 @@ def run_b200(a):
                           "ok": bool(errs and max(errs) <= 1e-8 and not not_conv and all(v["within_band"] for v in flagged.values())),
                           "flagged_ill_conditioned": {"count": len(flagged), "samples": flagged,
                                                       "rule": "rel-L2 <= 1e-8 + 4 x the direct solve's own half-ulp band"},
-                          "reported_not_converged": {"count": len(jobs) - len(conv), "rel_l2_vs_cpu_direct_solve": not_conv}}
+                          "reported_not_converged": {"count": len(jobs) - len(conv), "rel_l2_vs_cpu_direct_solve": not_conv},
+                          "images_note": "images are checked in tests/ (bit-exact to the raster oracle for the same u, within 1 LSB end "
+                                         "to end); that oracle is pinned to VTK's committed renders on INTERIOR pixels only -- VTK's "
+                                         "edge-pixel coverage rule is not recoverable without VTK (SURVEY A-16)"}
         line["cpu_baseline"] = {"value": len(jobs) / dt, "unit": "solves/s", "cores": 1, "kind": "port",
                                 "host_cores_available": os.cpu_count(),
                                 "sample": "first %d plate-conditions of the workload, %.1f s, reference-faithful "
