@@ -152,3 +152,44 @@ def test_every_context_option_is_documented_in_the_header():
     header = open(os.path.join(root, "include", "fea_b200.h")).read()
     missing = [k for k in sorted(keys) if '"%s"' % k not in header]
     assert not missing, missing
+
+
+def test_arena_device_addresses_and_descriptor_rebasing():
+    """Host logic of the pipelined upload (no GPU): arrays carved from a PinnedArena map to the same offsets of
+    its device copy, arrays from elsewhere do not; PackedConditions.use_device_copy rebases exactly the three
+    big arrays of the descriptor (xy, conn, mat_coords) and nothing else."""
+    from fea_diffusion_b200.solver import PackedConditions, PinnedArena
+
+    class FakeCtx:                      # the two calls PinnedArena makes on a context
+        def pinned_empty(self, shape, dtype):
+            return np.empty(shape, dtype)
+
+        def device_alloc(self, n):
+            self.n = n
+            return 0x7000_0000_0000
+
+        def device_upload(self, dev, host, nbytes):
+            self.uploaded = (dev, nbytes)
+
+    ctx = FakeCtx()
+    arena = PinnedArena(ctx, 1 << 20)
+    co, cn = cases.small_plate() if hasattr(cases, "small_plate") else (np.array([[0., 0.], [1., 0.], [0., 1.], [1., 1.]]),
+                                                                         np.array([[0, 1, 2], [1, 3, 2]], np.int32))
+    kw = dict(force_vertex_tags_magnitudes=[(2, (1.0, 0.0))], constraints_vertex_tags=[1, 3],
+              material_properties_to_vertices={(210000.0, 0.3): np.asarray(co, float)})
+    pc = PackedConditions([(co, cn)], [(0, kw), (0, kw)], alloc=arena.empty)
+    host_ptrs = {f: getattr(pc.desc, f) for f, _ in pc.desc._fields_}
+    assert arena.device_address(pc.xy) is None                      # nothing uploaded yet
+    arena.upload(ctx)
+    assert ctx.uploaded == (0x7000_0000_0000, arena.off) and arena.spilled == 0
+    base = arena.buf.ctypes.data
+    for a in (pc.xy, pc.conn, pc.mat_coords):
+        assert arena.device_address(a) == 0x7000_0000_0000 + (a.ctypes.data - base)
+    assert arena.device_address(np.zeros(4)) is None and arena.device_address(pc.mesh_vtx_off) is None
+    pc.use_device_copy(arena)
+    for f, _ in pc.desc._fields_:
+        v = getattr(pc.desc, f)
+        if f in ("xy", "conn", "mat_coords"):
+            assert v == 0x7000_0000_0000 + (getattr(pc, f).ctypes.data - base), f
+        else:
+            assert v == host_ptrs[f], f
